@@ -1,0 +1,283 @@
+/* CPU oracle for the neural BSDF sampler hot path -- plain C + OpenMP restatement.
+ *
+ * TEST INFRASTRUCTURE ONLY: used by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs, never by the product path.
+ *
+ * Same arithmetic as oracle/bsdf_oracle.py (which is the readable spec and carries the
+ * per-function reference citations); this file exists so that the checker finishes in seconds at
+ * N ~ 1e6 and so that the CPU baseline uses every host core.  One query per loop iteration,
+ * float32 throughout, closed-form forward-mode tangents instead of the reference's two autograd
+ * sweeps per step.
+ *
+ * Reference (fzy28/BSDF_diffusion_sampling @ f2b615c) lines followed:
+ *   pe()               rendering/utils/model.py:9-57 (positional_encoding_1)
+ *   base_eval()        rendering/utils/model.py:382-386 (14->16->4 with biases, SiLU)
+ *   logp_disk()        rendering/utils/model.py:393-398
+ *   logp_sph()         rendering/utils/model.py:293-298,308-317 + torch von_mises.py log I0 polynomials
+ *   flow_step()        rendering/utils/model.py:490-501 / 435-446 ; tangents replace
+ *                      rendering/utils/mlp_brdf_sampling.py:33-41
+ *   bsdf_oracle_sample rendering/utils/mlp_brdf_sampling.py:17-51 (disk), :106-140 (spherical)
+ *   bsdf_oracle_pdf    rendering/utils/mlp_brdf_sampling.py:69-103 (disk), :144-181 (spherical)
+ *   epilogues          rendering/brdf_measured_disk.py:69-82,112-124;
+ *                      rendering/brdf_measured_spherical.py:31-39,79-92,122-137;
+ *                      rendering/bsdf_myresult.py:69-84,115-130 (PARITY UNPINNED: needs Mitsuba)
+ *   bsdf_oracle_reflow learning_repo_cleanup/disk_domain_sampling.py:100-108,
+ *                      learning_repo_cleanup/spherical_domain_sampling.py:154-164 (fp32 module)
+ *
+ * Parity pin: tests/test_oracle_golden.py checks this library against tests/golden/*.npz, which
+ * were produced by the reference's own Python functions (tests/golden/make_golden.py).
+ *
+ * Build: gcc -O3 -fopenmp -shared -fPIC oracle/bsdf_oracle.c -o oracle/libbsdf_oracle.so -lm
+ */
+#include <math.h>
+#include <stdint.h>
+#include <float.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define MAXH 64
+#define PE5 22
+#define PE3 14
+
+static inline float sigmoidf_(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+static void pe(const float v[2], int L, float* out) {
+    out[0] = v[0]; out[1] = v[1];
+    float f = 1.0f;
+    for (int k = 0; k < L; ++k) {
+        out[2 + 4 * k + 0] = sinf(v[0] * f);
+        out[2 + 4 * k + 1] = sinf(v[1] * f);
+        out[2 + 4 * k + 2] = cosf(v[0] * f);
+        out[2 + 4 * k + 3] = cosf(v[1] * f);
+        f *= 2.0f;
+    }
+}
+
+/* base blob: w1[16*14], b1[16], wo[4*16], bo[4] */
+static void base_eval(const float* base, const float wi[2], float p[4]) {
+    float e[PE3], h[16];
+    pe(wi, 3, e);
+    const float *w1 = base, *b1 = base + 224, *wo = base + 240, *bo = base + 304;
+    for (int j = 0; j < 16; ++j) {
+        float z = 0.f;
+        for (int k = 0; k < PE3; ++k) z += e[k] * w1[j * PE3 + k];
+        z += b1[j];
+        h[j] = z * sigmoidf_(z);
+    }
+    for (int o = 0; o < 4; ++o) {
+        float z = 0.f;
+        for (int j = 0; j < 16; ++j) z += h[j] * wo[o * 16 + j];
+        p[o] = z + bo[o];
+    }
+}
+
+static float logp_disk(const float* base, const float x[2], const float wi[2]) {
+    float p[4];
+    base_eval(base, wi, p);
+    float e0 = (x[0] - p[0]) / expf(p[2]), e1 = (x[1] - p[1]) / expf(p[3]);
+    return (float)(-0.5 * 2 * log(2 * M_PI)) - (p[2] + p[3]) - 0.5f * (e0 * e0 + e1 * e1);
+}
+
+static float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+
+static float log_i0f(float x) {
+    static const float cs[7] = {1.0f, 3.5156229f, 3.0899424f, 1.2067492f, 0.2659732f, 0.360768e-1f, 0.45813e-2f};
+    static const float cl[9] = {0.39894228f, 0.1328592e-1f, 0.225319e-2f, -0.157565e-2f, 0.916281e-2f,
+                                -0.2057706e-1f, 0.2635537e-1f, -0.1647633e-1f, 0.392377e-2f};
+    if (x < 3.75f) {
+        float y = x / 3.75f; y = y * y;
+        float r = cs[6];
+        for (int i = 5; i >= 0; --i) r = cs[i] + y * r;
+        return logf(r);
+    }
+    float y = 3.75f / x, r = cl[8];
+    for (int i = 7; i >= 0; --i) r = cl[i] + y * r;
+    return x - 0.5f * logf(x) + logf(r);
+}
+
+static float logp_sph(const float* base, const float x[2], const float wi[2]) {
+    float p[4];
+    base_eval(base, wi, p);
+    float kappa = softplusf_(p[3]) + 1e-3f;
+    float e = (x[0] - p[0]) / (expf(p[1]) + 1e-3f);
+    float loggau = (float)(-0.5 * log(2 * M_PI)) - p[1] - 0.5f * e * e;
+    float logvon = kappa * cosf(x[1] - p[2]) - (float)log(2 * M_PI) - log_i0f(kappa);
+    return loggau + logvon;
+}
+
+/* One network evaluation with two tangent columns.  flow = W1[H*in] | W2..[H*H] | Wout[2*H]. */
+static void flow_step(const float* flow, int in_dim, int H, int n_hidden, int domain,
+                      const float x[2], float alpha, const float* pe_wi,
+                      float d[2], float du[2], float dv[2], int want_tangents) {
+    float inp[32], h[MAXH], u[MAXH], v[MAXH], h2[MAXH], u2[MAXH], v2[MAXH];
+    int k0;
+    float s = 0.f, c = 0.f;
+    if (domain == 0) { inp[0] = x[0]; inp[1] = x[1]; inp[2] = alpha; k0 = 3; }
+    else { s = sinf(x[1]); c = cosf(x[1]); inp[0] = x[0]; inp[1] = s; inp[2] = c; inp[3] = alpha; k0 = 4; }
+    for (int k = 0; k < PE5; ++k) inp[k0 + k] = pe_wi[k];
+    const float* W = flow;
+    for (int j = 0; j < H; ++j) {
+        float z = 0.f;
+        for (int k = 0; k < in_dim; ++k) z += inp[k] * W[j * in_dim + k];
+        float sg = sigmoidf_(z);
+        h[j] = z * sg;
+        if (want_tangents) {
+            float g = sg * (1.0f + z * (1.0f - sg));
+            u[j] = g * W[j * in_dim + 0];
+            v[j] = g * (domain == 0 ? W[j * in_dim + 1] : (c * W[j * in_dim + 1] - s * W[j * in_dim + 2]));
+        }
+    }
+    W += H * in_dim;
+    for (int l = 1; l < n_hidden; ++l) {
+        for (int j = 0; j < H; ++j) {
+            float z = 0.f, zu = 0.f, zv = 0.f;
+            const float* w = W + j * H;
+            for (int k = 0; k < H; ++k) z += h[k] * w[k];
+            float sg = sigmoidf_(z);
+            h2[j] = z * sg;
+            if (want_tangents) {
+                for (int k = 0; k < H; ++k) { zu += u[k] * w[k]; zv += v[k] * w[k]; }
+                float g = sg * (1.0f + z * (1.0f - sg));
+                u2[j] = g * zu; v2[j] = g * zv;
+            }
+        }
+        memcpy(h, h2, sizeof(float) * H);
+        if (want_tangents) { memcpy(u, u2, sizeof(float) * H); memcpy(v, v2, sizeof(float) * H); }
+        W += H * H;
+    }
+    for (int o = 0; o < 2; ++o) {
+        float z = 0.f, zu = 0.f, zv = 0.f;
+        for (int k = 0; k < H; ++k) {
+            z += h[k] * W[o * H + k];
+            if (want_tangents) { zu += u[k] * W[o * H + k]; zv += v[k] * W[o * H + k]; }
+        }
+        d[o] = z; du[o] = zu; dv[o] = zv;
+    }
+}
+
+static void euler(const float* flow, int in_dim, int H, int n_hidden, int domain, int T, int reverse,
+                  float x[2], const float wi[2], float* R_out) {
+    float e[PE5];
+    pe(wi, 5, e);
+    float R = 1.0f;
+    const float inv_t = (float)(1.0 / T), sgn = reverse ? -1.0f : 1.0f;
+    for (int t = 0; t < T; ++t) {
+        float alpha = (float)(reverse ? (1.0 - (double)t / T) : ((double)t / T));
+        float d[2], du[2], dv[2];
+        flow_step(flow, in_dim, H, n_hidden, domain, x, alpha, e, d, du, dv, 1);
+        float j00 = 1.0f + sgn * inv_t * du[0], j01 = sgn * inv_t * dv[0];
+        float j10 = sgn * inv_t * du[1], j11 = 1.0f + sgn * inv_t * dv[1];
+        float det = j00 * j11 - j01 * j10;
+        R = reverse ? R * det : R / det;
+        x[0] += sgn * inv_t * d[0];
+        x[1] += sgn * inv_t * d[1];
+    }
+    *R_out = R;
+}
+
+static void cart_to_spher(const float w[3], float out[2]) {
+    float r = sqrtf(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    out[0] = acosf(w[2] / (r + 1e-8f));
+    out[1] = atan2f(w[1], w[0]);
+}
+
+static float inv_sin_clamped(float x, float y, int use_abs) {
+    float s = sqrtf(fmaxf(x * x + y * y, 0.f));
+    if (use_abs) s = fabsf(s);
+    float inv = 1.0f / s;
+    return fminf(fmaxf(inv, 1.0f), FLT_MAX);
+}
+
+/* epilogue: 0 raw domain coords (x[n,2], pdf) ; 1 disk plugin ; 2 measured-spherical plugin ; 3 bsdf plugin
+ * wi is [n,2] domain coords for epilogue 0, [n,3] local-frame directions otherwise.
+ * x0 (replayed base sample, [n,2]) is REQUIRED: the oracle never draws random numbers itself. */
+int bsdf_oracle_sample(int domain, int epilogue, int T, int64_t n, const float* wi, const float* flow, int in_dim,
+                       int H, int n_hidden, const float* base, const float* x0, float* out_dir, float* out_pdf) {
+    if (!x0 || H > MAXH || in_dim > 32) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float w[2];
+        if (epilogue == 0) { w[0] = wi[2 * i]; w[1] = wi[2 * i + 1]; }
+        else if (epilogue == 1) { w[0] = wi[3 * i]; w[1] = wi[3 * i + 1]; }
+        else cart_to_spher(wi + 3 * i, w);
+        float x[2] = {x0[2 * i], x0[2 * i + 1]};
+        float p0 = expf(domain == 0 ? logp_disk(base, x, w) : logp_sph(base, x, w));
+        float R;
+        euler(flow, in_dim, H, n_hidden, domain, T, 0, x, w, &R);
+        float pdf = p0 * R;
+        if (epilogue == 0) {
+            out_dir[2 * i] = x[0]; out_dir[2 * i + 1] = x[1]; out_pdf[i] = pdf;
+        } else if (epilogue == 1) {
+            int valid = (x[0] * x[0] + x[1] * x[1]) < 0.995f;
+            if (!valid) { x[0] = 0.f; x[1] = 0.f; pdf = 0.f; }
+            float z = sqrtf(fmaxf(1.0f - (x[0] * x[0] + x[1] * x[1]), 0.f));
+            out_dir[3 * i] = x[0]; out_dir[3 * i + 1] = x[1]; out_dir[3 * i + 2] = z;
+            out_pdf[i] = pdf * z;
+        } else {
+            float st = sinf(x[0]), ct = cosf(x[0]), sp = sinf(x[1]), cp = cosf(x[1]);
+            if (!(st > 0.00005f)) pdf = 0.f;
+            if (epilogue == 2 && !(ct > 0.f)) pdf = 0.f;
+            float ox = cp * st, oy = sp * st;
+            out_dir[3 * i] = ox; out_dir[3 * i + 1] = oy; out_dir[3 * i + 2] = ct;
+            out_pdf[i] = pdf * inv_sin_clamped(ox, oy, epilogue == 3);
+        }
+    }
+    return 0;
+}
+
+int bsdf_oracle_pdf(int domain, int epilogue, int T, int64_t n, const float* wo, const float* wi, const float* flow,
+                    int in_dim, int H, int n_hidden, const float* base, float* out_pdf) {
+    if (H > MAXH || in_dim > 32) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float w[2], x[2];
+        if (epilogue == 0) { w[0] = wi[2 * i]; w[1] = wi[2 * i + 1]; x[0] = wo[2 * i]; x[1] = wo[2 * i + 1]; }
+        else if (epilogue == 1) { w[0] = wi[3 * i]; w[1] = wi[3 * i + 1]; x[0] = wo[3 * i]; x[1] = wo[3 * i + 1]; }
+        else { cart_to_spher(wi + 3 * i, w); cart_to_spher(wo + 3 * i, x); }
+        float theta_o = x[0];
+        float R;
+        euler(flow, in_dim, H, n_hidden, domain, T, 1, x, w, &R);
+        float pdf = expf(domain == 0 ? logp_disk(base, x, w) : logp_sph(base, x, w)) * R;
+        if (epilogue == 1) {
+            int ok = (wi[3 * i + 2] > 0.f) && (wo[3 * i + 2] > 0.f);
+            pdf = ok ? pdf * wo[3 * i + 2] : 0.f;
+        } else if (epilogue == 2) {
+            if (!(sinf(theta_o) > 0.00005f)) pdf = 0.f;
+            int ok = (wi[3 * i + 2] > 0.f) && (wo[3 * i + 2] > 0.f);
+            pdf = ok ? pdf * inv_sin_clamped(wo[3 * i], wo[3 * i + 1], 0) : 0.f;
+        } else if (epilogue == 3) {
+            pdf = pdf * inv_sin_clamped(wo[3 * i], wo[3 * i + 1], 1);
+        }
+        out_pdf[i] = pdf;
+    }
+    return 0;
+}
+
+/* forward-only Euler (dosampling) with the fp32 module. */
+int bsdf_oracle_reflow(int domain, int T, int64_t n, const float* x0, const float* wi, const float* flow, int in_dim,
+                       int H, int n_hidden, float* out_x) {
+    if (H > MAXH || in_dim > 32) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        float w[2] = {wi[2 * i], wi[2 * i + 1]}, x[2] = {x0[2 * i], x0[2 * i + 1]}, e[PE5];
+        pe(w, 5, e);
+        const float inv_t = (float)(1.0 / T);
+        for (int t = 0; t < T; ++t) {
+            float d[2], du[2], dv[2];
+            flow_step(flow, in_dim, H, n_hidden, domain, x, (float)((double)t / T), e, d, du, dv, 0);
+            x[0] += inv_t * d[0]; x[1] += inv_t * d[1];
+        }
+        out_x[2 * i] = x[0]; out_x[2 * i + 1] = x[1];
+    }
+    return 0;
+}
+
+int bsdf_oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
