@@ -1,0 +1,72 @@
+"""ctypes binding of libbsdfdiff.so (include/bsdfdiff.h).
+
+The library is the product: there is no Python/PyTorch fallback.  If it has not been built
+(``python -m bsdf_diffusion_sampling_b200.build``) importing this module raises ``ImportError``;
+if it is called without a CUDA device the entry points raise ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbsdfdiff.so")
+
+# constants mirrored from include/bsdfdiff.h
+DISK, SPHERICAL = 0, 1
+EPI_RAW, EPI_DISK, EPI_SPHERICAL, EPI_BSDF = 0, 1, 2, 3
+PREC_FP32, PREC_TC16 = 0, 1
+BASE_FLOATS = 308
+ABI_VERSION = 1
+
+EXPORTS = [
+    "bsdfdiff_abi_version", "bsdfdiff_error_string", "bsdfdiff_last_cuda_error", "bsdfdiff_device_info",
+    "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn",
+    "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
+]
+
+_c = ctypes
+_vp, _i, _i64, _u64 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build it with `python -m bsdf_diffusion_sampling_b200.build` "
+            "(nvcc, sm_100a). There is no CPU / PyTorch fallback for this package.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.bsdfdiff_abi_version.restype = _i
+    lib.bsdfdiff_error_string.restype = _c.c_char_p
+    lib.bsdfdiff_error_string.argtypes = [_i]
+    lib.bsdfdiff_last_cuda_error.restype = _i
+    lib.bsdfdiff_device_info.argtypes = [_c.POINTER(_i)] * 3
+    lib.bsdfdiff_packed_flow_bytes.restype = _c.c_size_t
+    lib.bsdfdiff_packed_flow_bytes.argtypes = [_i, _i, _i]
+    lib.bsdfdiff_pack_flow.argtypes = [_c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i), _i, _vp]
+    lib.bsdfdiff_pack_flow_tcnn.argtypes = [_vp, _i, _i, _i, _i, _vp]
+    lib.bsdfdiff_sample.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _u64, _u64, _i64,
+                                    _vp, _vp, _vp, _vp]
+    lib.bsdfdiff_pdf.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]
+    lib.bsdfdiff_flow_forward.argtypes = [_i, _i, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _u64, _u64, _i64,
+                                          _vp, _vp, _vp]
+    lib.bsdfdiff_mlp_forward.argtypes = [_i, _i64, _vp, _i, _vp, _i, _i, _vp, _vp]
+    for name in ("bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_sample", "bsdfdiff_pdf",
+                 "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward", "bsdfdiff_device_info"):
+        getattr(lib, name).restype = _i
+    if lib.bsdfdiff_abi_version() != ABI_VERSION:
+        raise ImportError("libbsdfdiff.so ABI version mismatch; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+class BsdfDiffError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib.bsdfdiff_error_string(rc).decode()
+        extra = f" (cudaError {lib.bsdfdiff_last_cuda_error()})" if rc == -3 else ""
+        raise BsdfDiffError(f"{what}: {msg}{extra}")

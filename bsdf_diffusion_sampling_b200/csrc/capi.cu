@@ -1,0 +1,271 @@
+// extern "C" entry points of libbsdfdiff.so (declared in include/bsdfdiff.h) and the host-side
+// weight packer.  No torch types; plain pointers, sizes and a cudaStream_t passed as void*.
+#include "../../include/bsdfdiff.h"
+#include "common.cuh"
+
+#include <cstring>
+#include <vector>
+
+using namespace bsdfdiff;
+
+static thread_local int g_last_cuda_error = 0;
+
+static int fail_cuda() {
+    g_last_cuda_error = (int)cudaGetLastError();
+    return BSDFDIFF_ECUDA;
+}
+
+extern "C" int bsdfdiff_abi_version(void) { return BSDFDIFF_ABI_VERSION; }
+
+extern "C" const char* bsdfdiff_error_string(int code) {
+    switch (code) {
+        case BSDFDIFF_OK: return "ok";
+        case BSDFDIFF_EINVAL: return "invalid argument";
+        case BSDFDIFF_EUNSUPPORTED: return "shape not supported by the requested precision path";
+        case BSDFDIFF_ECUDA: return "CUDA runtime error";
+        case BSDFDIFF_ENOTSM100: return "device is not compute capability 10.x (sm_100a required)";
+        default: return "unknown error";
+    }
+}
+
+extern "C" int bsdfdiff_last_cuda_error(void) { return g_last_cuda_error; }
+
+extern "C" int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return fail_cuda();
+    int a = 0, b = 0, c = 0;
+    cudaDeviceGetAttribute(&a, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&b, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&c, cudaDevAttrComputeCapabilityMinor, dev);
+    if (sm_count) *sm_count = a;
+    if (cc_major) *cc_major = b;
+    if (cc_minor) *cc_minor = c;
+    return BSDFDIFF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// packing
+// ------------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t aux_floats(int H) { return 3 * (size_t)H; }
+
+extern "C" size_t bsdfdiff_packed_flow_bytes(int in_dim, int hidden, int n_hidden) {
+    if (in_dim < 1 || in_dim > 32 || (hidden != 32 && hidden != 64) || n_hidden < 1 || n_hidden > 16) return 0;
+    size_t b = sizeof(PackedHeader);
+    b += align_up(sizeof(float) * f32_image_floats(in_dim, hidden, n_hidden), 128);
+    b += align_up(sizeof(__half) * f16_image_halves(hidden, n_hidden), 128);
+    b += align_up(sizeof(float) * aux_floats(hidden), 128);
+    return b;
+}
+
+// UMMA canonical K-major, no swizzle: 8x8 core matrices of 128 contiguous bytes; core matrices
+// ordered K-chunk-major then N-group (LBO = N*16 bytes between K chunks, SBO = 128 bytes between
+// 8-row groups).  Returns the element index of (n,k) inside an [N x K] operand image.
+static inline size_t umma_kmajor_index(int n, int k, int N) {
+    return ((size_t)(k / 8) * (N / 8) + (size_t)(n / 8)) * 64 + (size_t)(n % 8) * 8 + (size_t)(k % 8);
+}
+
+// Column map of the tensor-core first layer (K = 32): hi parts, PE5(wi), then the lo parts of the
+// fp32 state so the fp16 A operand carries the state to ~2^-22 (see flow_tc.cu).
+static void tc_layer1_source_columns(int domain, int in_dim, int src[32]) {
+    for (int k = 0; k < 32; ++k) src[k] = -1;
+    for (int k = 0; k < in_dim; ++k) src[k] = k;
+    const int n_state = (domain == kDisk) ? 3 : 4;                 // x0,x1,alpha | theta,sin,cos,alpha
+    if (in_dim + n_state <= 32)
+        for (int s = 0; s < n_state; ++s) src[in_dim + s] = s;
+}
+
+static int pack_from_layers(const std::vector<const float*>& Ws, const std::vector<int>& rows,
+                            const std::vector<int>& cols, void* packed_out) {
+    const int n_layers = (int)Ws.size();
+    if (n_layers < 2 || !packed_out) return BSDFDIFF_EINVAL;
+    const int H = rows[0], in_dim = cols[0], n_hidden = n_layers - 1;
+    if ((H != 32 && H != 64) || in_dim < 1 || in_dim > 32) return BSDFDIFF_EUNSUPPORTED;
+    for (int l = 1; l < n_hidden; ++l)
+        if (rows[l] != H || cols[l] != H) return BSDFDIFF_EINVAL;
+    if (rows[n_layers - 1] != 2 || cols[n_layers - 1] != H) return BSDFDIFF_EINVAL;
+    const int domain = (in_dim == 26) ? kSpherical : kDisk;
+
+    const size_t total = bsdfdiff_packed_flow_bytes(in_dim, H, n_hidden);
+    if (!total) return BSDFDIFF_EUNSUPPORTED;
+    unsigned char* out = static_cast<unsigned char*>(packed_out);
+    std::memset(out, 0, total);
+    PackedHeader hdr{};
+    hdr.magic = kMagic; hdr.in_dim = in_dim; hdr.hidden = H; hdr.n_hidden = n_hidden; hdr.domain = domain;
+    hdr.off_f32 = sizeof(PackedHeader);
+    hdr.f32_bytes = (uint32_t)(sizeof(float) * f32_image_floats(in_dim, H, n_hidden));
+    hdr.off_f16 = hdr.off_f32 + (uint32_t)align_up(hdr.f32_bytes, 128);
+    hdr.f16_bytes = (uint32_t)(sizeof(__half) * f16_image_halves(H, n_hidden));
+    hdr.reserved[0] = hdr.off_f16 + (uint32_t)align_up(hdr.f16_bytes, 128);   // aux offset
+    hdr.reserved[1] = (uint32_t)(sizeof(float) * aux_floats(H));
+    hdr.total_bytes = (uint32_t)total;
+    std::memcpy(out, &hdr, sizeof(hdr));
+
+    // fp32 image, transposed to [k][j]
+    float* f = reinterpret_cast<float*>(out + hdr.off_f32);
+    for (int l = 0; l < n_layers; ++l) {
+        const int R = rows[l], C = cols[l];
+        for (int j = 0; j < R; ++j)
+            for (int k = 0; k < C; ++k) f[(size_t)k * R + j] = Ws[l][(size_t)j * C + k];
+        f += (size_t)R * C;
+    }
+
+    // fp16 tensor-core image
+    __half* h = reinterpret_cast<__half*>(out + hdr.off_f16);
+    int src[32];
+    tc_layer1_source_columns(domain, in_dim, src);
+    for (int n = 0; n < H; ++n)
+        for (int k = 0; k < 32; ++k) {
+            const float w = (src[k] >= 0) ? 0.5f * Ws[0][(size_t)n * in_dim + src[k]] : 0.0f;
+            h[umma_kmajor_index(n, k, H)] = __float2half_rn(w);
+        }
+    h += (size_t)H * 32;
+    for (int l = 1; l < n_hidden; ++l) {
+        for (int n = 0; n < H; ++n)
+            for (int k = 0; k < H; ++k)
+                h[umma_kmajor_index(n, k, H)] = __float2half_rn(0.5f * Ws[l][(size_t)n * H + k]);
+        h += (size_t)H * H;
+    }
+    for (int n = 0; n < 16; ++n)
+        for (int k = 0; k < H; ++k) {
+            const float w = (n < 2) ? Ws[n_layers - 1][(size_t)n * H + k] : 0.0f;
+            h[umma_kmajor_index(n, k, 16)] = __float2half_rn(w);
+        }
+
+    // aux: 0.5 * W1[:,0], 0.5 * W1[:,1], 0.5 * W1[:,2]  (first-layer tangent seeds, fp16-rounded like
+    // the operand image so value and tangent paths see the same weights)
+    float* aux = reinterpret_cast<float*>(out + hdr.reserved[0]);
+    for (int c = 0; c < 3; ++c)
+        for (int j = 0; j < H; ++j)
+            aux[c * H + j] = (c < in_dim) ? __half2float(__float2half_rn(0.5f * Ws[0][(size_t)j * in_dim + c])) : 0.0f;
+    return BSDFDIFF_OK;
+}
+
+extern "C" int bsdfdiff_pack_flow(const float* const* layer_ptrs, const int* rows, const int* cols, int n_layers,
+                                  void* packed_out) {
+    if (!layer_ptrs || !rows || !cols || n_layers < 2) return BSDFDIFF_EINVAL;
+    std::vector<const float*> W(layer_ptrs, layer_ptrs + n_layers);
+    for (auto p : W) if (!p) return BSDFDIFF_EINVAL;
+    return pack_from_layers(W, std::vector<int>(rows, rows + n_layers), std::vector<int>(cols, cols + n_layers),
+                            packed_out);
+}
+
+// tcnn flat layout (learning_repo_cleanup/utils/utils.py:13-23): W1 padded to in+16-in%16 columns,
+// hidden layers as-is, output padded to out+16-out%16 rows; all row-major.
+extern "C" int bsdfdiff_pack_flow_tcnn(const float* p, int in_dim, int out_dim, int hidden, int n_hidden,
+                                       void* packed_out) {
+    if (!p || out_dim != 2 || n_hidden < 1) return BSDFDIFF_EINVAL;
+    const int in_pad = in_dim + 16 - in_dim % 16;
+    std::vector<std::vector<float>> store;
+    std::vector<const float*> W;
+    std::vector<int> rows, cols;
+    std::vector<float> w1((size_t)hidden * in_dim);
+    for (int j = 0; j < hidden; ++j)
+        for (int k = 0; k < in_dim; ++k) w1[(size_t)j * in_dim + k] = p[(size_t)j * in_pad + k];
+    store.push_back(std::move(w1));
+    rows.push_back(hidden); cols.push_back(in_dim);
+    const float* q = p + (size_t)hidden * in_pad;
+    for (int l = 1; l < n_hidden; ++l) {
+        store.emplace_back(q, q + (size_t)hidden * hidden);
+        rows.push_back(hidden); cols.push_back(hidden);
+        q += (size_t)hidden * hidden;
+    }
+    store.emplace_back(q, q + (size_t)2 * hidden);      // first 2 of the padded output rows
+    rows.push_back(2); cols.push_back(hidden);
+    for (auto& v : store) W.push_back(v.data());
+    return pack_from_layers(W, rows, cols, packed_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+static int dispatch(int precision, const FlowParams& P, cudaStream_t stream) {
+    int rc;
+    if (precision == BSDFDIFF_PREC_FP32 || P.T == 0) rc = launch_simt(P, stream);
+    else if (precision == BSDFDIFF_PREC_TC16) rc = launch_tc(P, stream);
+    else return BSDFDIFF_EINVAL;
+    if (rc == -3) return fail_cuda();
+    return rc;
+}
+
+static int fill_shape(FlowParams& P, const void* flow_packed, int domain, int hidden, int n_hidden) {
+    if ((hidden != 32 && hidden != 64) || n_hidden < 1 || n_hidden > 16) return BSDFDIFF_EUNSUPPORTED;
+    P.in_dim = (domain == kDisk) ? 25 : 26; P.hidden = hidden; P.n_hidden = n_hidden;
+    P.flow = static_cast<const unsigned char*>(flow_packed);
+    return 0;
+}
+
+extern "C" int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
+                               const float* wi, const void* flow_packed, int hidden, int n_hidden,
+                               const float* base_params, const float* x0_replay, uint64_t seed, uint64_t offset, int64_t first_index,
+                               float* out_dir, float* out_pdf, float* out_x0, void* cuda_stream) {
+    // T == 0 with flow_packed == NULL evaluates the base distribution alone (D_base.sample / log_prob)
+    if (n < 0 || T < 0 || ((T == 0) != (flow_packed == nullptr)) || !base_params ||
+        (domain != kDisk && domain != kSpherical) ||
+        epilogue < 0 || epilogue > 3 || (epilogue == kEpiDisk && domain != kDisk) ||
+        (epilogue >= kEpiSpherical && domain != kSpherical))
+        return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    if (!wi || !out_dir || !out_pdf) return BSDFDIFF_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    FlowParams P{};
+    P.domain = domain; P.mode = kModeSample; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
+    P.wi = wi; P.x0 = x0_replay; P.base = base_params; P.seed = seed; P.offset = offset; P.first_index = first_index;
+    P.out_dir = out_dir; P.out_pdf = out_pdf; P.out_x0 = out_x0;
+    int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
+    if (rc) return rc;
+    return dispatch(precision, P, stream);
+}
+
+extern "C" int bsdfdiff_pdf(int precision, int domain, int epilogue, int T, int64_t n,
+                            const float* wo, const float* wi, const void* flow_packed, int hidden, int n_hidden,
+                            const float* base_params, float* out_pdf, void* cuda_stream) {
+    if (n < 0 || T < 0 || ((T == 0) != (flow_packed == nullptr)) || !base_params ||
+        (domain != kDisk && domain != kSpherical) ||
+        epilogue < 0 || epilogue > 3 || (epilogue == kEpiDisk && domain != kDisk) ||
+        (epilogue >= kEpiSpherical && domain != kSpherical))
+        return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    if (!wi || !wo || !out_pdf) return BSDFDIFF_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    FlowParams P{};
+    P.domain = domain; P.mode = kModePdf; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
+    P.wi = wi; P.wo = wo; P.base = base_params; P.out_pdf = out_pdf;
+    int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
+    if (rc) return rc;
+    return dispatch(precision, P, stream);
+}
+
+extern "C" int bsdfdiff_flow_forward(int precision, int domain, int T, int64_t n, const float* wi, int64_t wi_repeat,
+                                     const void* flow_packed, int hidden, int n_hidden, const float* base_params,
+                                     const float* x0, uint64_t seed, uint64_t offset, int64_t first_index,
+                                     float* out_x, float* out_x0, void* cuda_stream) {
+    if (n < 0 || T < 1 || !flow_packed || (domain != kDisk && domain != kSpherical) || wi_repeat < 1 ||
+        (!x0 && !base_params))
+        return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    if (!wi || !out_x) return BSDFDIFF_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    FlowParams P{};
+    P.domain = domain; P.mode = kModeForward; P.epilogue = kEpiRaw; P.T = T; P.n = n; P.wi_repeat = wi_repeat;
+    P.wi = wi; P.x0 = x0; P.base = base_params; P.seed = seed; P.offset = offset; P.first_index = first_index;
+    P.out_dir = out_x; P.out_x0 = out_x0;
+    int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
+    if (rc) return rc;
+    return dispatch(precision, P, stream);
+}
+
+extern "C" int bsdfdiff_mlp_forward(int precision, int64_t n, const float* in, int in_dim, const void* flow_packed,
+                                    int hidden, int n_hidden, float* out, void* cuda_stream) {
+    if (n < 0 || !flow_packed) return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    if (!in || !out) return BSDFDIFF_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    if (in_dim < 1 || in_dim > 32) return BSDFDIFF_EINVAL;
+    (void)precision;   // the single-forward op is HBM-bound (104+ B/row in, 8 B/row out): fp32 CUDA cores suffice
+    int rc = launch_mlp_forward_simt(n, in, in_dim, static_cast<const unsigned char*>(flow_packed), hidden,
+                                     n_hidden, out, stream);
+    if (rc == -3) return fail_cuda();
+    return rc;
+}

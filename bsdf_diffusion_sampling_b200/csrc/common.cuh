@@ -1,0 +1,306 @@
+// Shared device/host definitions for libbsdfdiff: packed-weight blob layout, launch parameters,
+// Philox4x32-10, base-distribution net, domain mappings and plugin epilogues.
+//
+// Arithmetic spec: SURVEY.md Appendix A (validated against the reference's autograd path).
+// Reference lines are cited next to each function.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace bsdfdiff {
+
+constexpr int kDisk = 0, kSpherical = 1;
+constexpr int kEpiRaw = 0, kEpiDisk = 1, kEpiSpherical = 2, kEpiBsdf = 3;
+constexpr int kModeSample = 0, kModePdf = 1, kModeForward = 2;
+constexpr int kBaseFloats = 308;
+constexpr int kPE5 = 22;           // 2 + 4*5
+constexpr int kPE3 = 14;           // 2 + 4*3
+constexpr uint32_t kMagic = 0xB5DFD1F0u;
+
+// ---------------------------------------------------------------------------------------------
+// Packed flow-net blob (built on the host by bsdfdiff_pack_flow, resident in HBM, staged into
+// shared memory once per persistent CTA).
+//   [header 64 B]
+//   [fp32 image]  layer-major, each layer TRANSPOSED to [k][j] (input-major) so that a warp reads
+//                 consecutive output neurons j as float4 broadcasts:
+//                 W1t [in_dim][H], W2t.. [H][H], Woutt [H][2]
+//   [fp16 image]  tensor-core B operands, one per layer, in the UMMA canonical K-major no-swizzle
+//                 core-matrix layout (8 rows x 16 B per core matrix):
+//                 byte(n,k) = ((k/8)*(N/8) + n/8)*128 + (n%8)*16 + (k%8)*2
+//                 first layer K padded to 32 with hi/lo split columns (see flow_tc.cu), output layer
+//                 N padded to 16.  All TC weights pre-scaled by 0.5 except the output layer
+//                 (tanh-form sigmoid: the MMA produces z/2 directly; see flow_tc.cu).
+// ---------------------------------------------------------------------------------------------
+struct PackedHeader {
+    uint32_t magic;
+    int32_t in_dim;       // 25 | 26 (or arbitrary <= 32 for tcnn-style nets)
+    int32_t hidden;       // 32 | 64
+    int32_t n_hidden;     // number of hidden layers (3 disk, 4 spherical, 6 reflow-complex)
+    int32_t domain;       // kDisk | kSpherical
+    uint32_t off_f32;     // byte offset of the fp32 image
+    uint32_t f32_bytes;
+    uint32_t off_f16;     // byte offset of the fp16 image
+    uint32_t f16_bytes;
+    uint32_t total_bytes;
+    uint32_t reserved[6];
+};
+static_assert(sizeof(PackedHeader) == 64, "header must be 64 bytes");
+
+__host__ __device__ inline int f32_image_floats(int in_dim, int H, int n_hidden) {
+    return in_dim * H + (n_hidden - 1) * H * H + 2 * H;
+}
+// fp16 image: first layer [H x 32], hidden [H x H] x (n_hidden-1), output [16 x H]
+__host__ __device__ inline int f16_image_halves(int H, int n_hidden) {
+    return H * 32 + (n_hidden - 1) * H * H + 16 * H;
+}
+
+struct FlowParams {
+    int domain, mode, epilogue, T;
+    int in_dim, hidden, n_hidden;
+    long long n;
+    long long wi_repeat;          // query i reads wi[i / wi_repeat]
+    const float* wi;              // [.,2] or [.,3]
+    const float* wo;              // pdf mode
+    const float* x0;              // replayed base sample / reflow start (may be null)
+    const unsigned char* flow;    // packed blob (device)
+    const float* base;            // 308 floats (device) or null (forward mode with x0 given)
+    unsigned long long seed, offset;
+    long long first_index;
+    float* out_dir;               // [n,2] or [n,3]
+    float* out_pdf;               // [n]
+    float* out_x0;                // optional [n,2]
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter = (index lo, index hi, offset lo + round, offset hi)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0; key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ uint4 philox_draw(unsigned long long seed, unsigned long long offset,
+                                             long long index, uint32_t round) {
+    unsigned long long off = offset + round;
+    uint4 c = make_uint4((uint32_t)index, (uint32_t)((unsigned long long)index >> 32),
+                         (uint32_t)off, (uint32_t)(off >> 32));
+    return philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+// uniform in (0,1), 24 bits
+__device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    float r = sqrtf(-2.0f * logf(u01(a)));
+    float s, c;
+    sincospif(2.0f * u01(b), &s, &c);
+    n0 = r * c; n1 = r * s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// math helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sigmoid_precise(float z) { return 1.0f / (1.0f + expf(-z)); }
+
+// [v, sin(2^k v), cos(2^k v)]_k, frequency-major, sin before cos, then component (model.py:26,48-57)
+template <int L>
+__device__ __forceinline__ void positional_encoding(float v0, float v1, float* out) {
+    out[0] = v0; out[1] = v1;
+    float f = 1.0f;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+        float s0, c0, s1, c1;
+        sincosf(v0 * f, &s0, &c0);
+        sincosf(v1 * f, &s1, &c1);
+        out[2 + 4 * k + 0] = s0; out[2 + 4 * k + 1] = s1;
+        out[2 + 4 * k + 2] = c0; out[2 + 4 * k + 3] = c1;
+        f *= 2.0f;
+    }
+}
+
+// base net p = Wo silu(W1 PE3(wi) + b1) + bo  (rendering/utils/model.py:382-386); blob in smem/global
+__device__ __forceinline__ void base_eval(const float* __restrict__ b, float w0, float w1, float p[4]) {
+    float e[kPE3];
+    positional_encoding<3>(w0, w1, e);
+    p[0] = b[304]; p[1] = b[305]; p[2] = b[306]; p[3] = b[307];
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+        float z = b[224 + j];
+#pragma unroll
+        for (int k = 0; k < kPE3; ++k) z = fmaf(e[k], b[j * kPE3 + k], z);
+        float h = z * sigmoid_precise(z);
+        p[0] = fmaf(h, b[240 + j], p[0]);
+        p[1] = fmaf(h, b[256 + j], p[1]);
+        p[2] = fmaf(h, b[272 + j], p[2]);
+        p[3] = fmaf(h, b[288 + j], p[3]);
+    }
+}
+
+__device__ __forceinline__ float softplus_torch(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+
+// torch/distributions/von_mises.py _log_modified_bessel_fn(order=0)
+__device__ __forceinline__ float log_i0(float x) {
+    if (x < 3.75f) {
+        float y = x / 3.75f; y = y * y;
+        float r = 0.45813e-2f;
+        r = fmaf(y, r, 0.360768e-1f); r = fmaf(y, r, 0.2659732f); r = fmaf(y, r, 1.2067492f);
+        r = fmaf(y, r, 3.0899424f);   r = fmaf(y, r, 3.5156229f); r = fmaf(y, r, 1.0f);
+        return logf(r);
+    }
+    float y = 3.75f / x;
+    float r = 0.392377e-2f;
+    r = fmaf(y, r, -0.1647633e-1f); r = fmaf(y, r, 0.2635537e-1f); r = fmaf(y, r, -0.2057706e-1f);
+    r = fmaf(y, r, 0.916281e-2f);   r = fmaf(y, r, -0.157565e-2f); r = fmaf(y, r, 0.225319e-2f);
+    r = fmaf(y, r, 0.1328592e-1f);  r = fmaf(y, r, 0.39894228f);
+    return x - 0.5f * logf(x) + logf(r);
+}
+
+constexpr float kLog2Pi = 1.8378770664093453f;
+
+// log-density of the base distribution at x given the 4 base-net outputs.
+//   disk:      model.py:393-398   (diagonal Gaussian, loc=p[0:2], log_scale=p[2:4])
+//   spherical: model.py:293-298,308-317 (Gaussian(theta) x vonMises(phi); normaliser uses log_scale as-is)
+__device__ __forceinline__ float base_logprob(int domain, const float p[4], float x0, float x1) {
+    if (domain == kDisk) {
+        float e0 = (x0 - p[0]) / expf(p[2]), e1 = (x1 - p[1]) / expf(p[3]);
+        return -kLog2Pi - (p[2] + p[3]) - 0.5f * (e0 * e0 + e1 * e1);
+    }
+    float kappa = softplus_torch(p[3]) + 1e-3f;
+    float e = (x0 - p[0]) / (expf(p[1]) + 1e-3f);
+    float loggau = -0.5f * kLog2Pi - p[1] - 0.5f * e * e;
+    float logvon = kappa * cosf(x1 - p[2]) - kLog2Pi - log_i0(kappa);
+    return loggau + logvon;
+}
+
+// Draw the base sample with Philox.
+//   disk:      x = loc + eps * exp(log_scale)                         (model.py:387-392)
+//   spherical: theta = loc + eps*(exp(ls)+1e-3); phi ~ vonMises(mu,kappa) by Best & Fisher (1979)
+//              rejection, wrapped to [-pi,pi)                          (model.py:299-307, torch von_mises.py)
+//   The proposal parameter r is evaluated with a cancellation-free rearrangement so fp32 suffices
+//   (torch switches to fp64 because its formula cancels for small kappa).
+__device__ __forceinline__ void base_draw(int domain, const float p[4], unsigned long long seed,
+                                          unsigned long long offset, long long index, float& x0, float& x1) {
+    uint4 r4 = philox_draw(seed, offset, index, 0);
+    float n0, n1;
+    box_muller(r4.x, r4.y, n0, n1);
+    if (domain == kDisk) {
+        x0 = fmaf(n0, expf(p[2]), p[0]);
+        x1 = fmaf(n1, expf(p[3]), p[1]);
+        return;
+    }
+    x0 = fmaf(n0, expf(p[1]) + 1e-3f, p[0]);
+    const float kappa = softplus_torch(p[3]) + 1e-3f, mu = p[2];
+    const float s = sqrtf(fmaf(4.0f * kappa, kappa, 1.0f));
+    const float tau = 1.0f + s;
+    const float rho = (tau * 2.0f * kappa) / ((s + 1.0f) * (tau + sqrtf(2.0f * tau)));
+    const float r = (1.0f + rho * rho) / (2.0f * rho);
+    float phi = 0.0f;
+    for (uint32_t round = 1; round <= 64; ++round) {                // acceptance >= ~0.66 per round
+        uint4 q = philox_draw(seed, offset, index, round);
+        float z = cospif(u01(q.x));
+        float f = (1.0f + r * z) / (r + z);
+        float cc = kappa * (r - f);
+        float u2 = u01(q.y);
+        phi = ((q.z & 0x80000000u) ? 1.0f : -1.0f) * acosf(fminf(fmaxf(f, -1.0f), 1.0f));
+        if ((cc * (2.0f - cc) - u2 > 0.0f) || (logf(cc / u2) + 1.0f - cc >= 0.0f)) break;
+    }
+    float y = phi + 3.14159265358979f + mu;
+    y = y - 6.28318530717959f * floorf(y * 0.159154943091895f);   // python-style modulo
+    x1 = y - 3.14159265358979f;
+}
+
+// rendering/brdf_measured_spherical.py:35-39
+__device__ __forceinline__ void cart_to_spher(float x, float y, float z, float& theta, float& phi) {
+    float r = sqrtf(x * x + y * y + z * z);
+    theta = acosf(z / (r + 1e-8f));
+    phi = atan2f(y, x);
+}
+
+// dr.clamp(1/sin_theta(wo), 1, FLT_MAX)  (brdf_measured_spherical.py:89-91; bsdf_myresult.py:81)
+__device__ __forceinline__ float inv_sin_clamped(float wx, float wy) {
+    float s = sqrtf(fmaxf(wx * wx + wy * wy, 0.0f));
+    return fminf(fmaxf(1.0f / s, 1.0f), FLT_MAX);
+}
+
+// Load one query's conditioning (domain coords) from the caller's wi tensor.
+__device__ __forceinline__ void load_wi(const FlowParams& P, long long i, float& w0, float& w1, float& wz) {
+    long long q = (P.wi_repeat > 1) ? i / P.wi_repeat : i;
+    if (P.epilogue == kEpiRaw) {
+        float2 w = reinterpret_cast<const float2*>(P.wi)[q];
+        w0 = w.x; w1 = w.y; wz = 1.0f;
+    } else {
+        float a = P.wi[3 * q], b = P.wi[3 * q + 1], c = P.wi[3 * q + 2];
+        wz = c;
+        if (P.epilogue == kEpiDisk) { w0 = a; w1 = b; }            // brdf_measured_disk.py:66-67
+        else cart_to_spher(a, b, c, w0, w1);                        // brdf_measured_spherical.py:76-77
+    }
+}
+
+// Start state of the reverse (pdf) flow from the caller's wo tensor; woz/sin flag for the masks.
+__device__ __forceinline__ void load_wo(const FlowParams& P, long long i, float& x0, float& x1,
+                                        float& wox, float& woy, float& woz) {
+    if (P.epilogue == kEpiRaw) {
+        float2 w = reinterpret_cast<const float2*>(P.wo)[i];
+        x0 = w.x; x1 = w.y; wox = woy = 0.0f; woz = 1.0f;
+    } else {
+        wox = P.wo[3 * i]; woy = P.wo[3 * i + 1]; woz = P.wo[3 * i + 2];
+        if (P.epilogue == kEpiDisk) { x0 = wox; x1 = woy; }        // brdf_measured_disk.py:118-120
+        else cart_to_spher(wox, woy, woz, x0, x1);                  // brdf_measured_spherical.py:131-133
+    }
+}
+
+// Final mapping for sample(): domain state -> outgoing direction + solid-angle pdf (tensor part of
+// MyBSDF.sample before the ground-truth firefly clamp).
+__device__ __forceinline__ void store_sample(const FlowParams& P, long long i, float x0, float x1, float pdf) {
+    if (P.epilogue == kEpiRaw) {
+        reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
+        P.out_pdf[i] = pdf;
+        return;
+    }
+    float ox, oy, oz;
+    if (P.epilogue == kEpiDisk) {                                   // brdf_measured_disk.py:69-82
+        bool valid = (x0 * x0 + x1 * x1) < 0.995f;
+        if (!valid) { x0 = 0.0f; x1 = 0.0f; pdf = 0.0f; }
+        oz = sqrtf(fmaxf(1.0f - (x0 * x0 + x1 * x1), 0.0f));        // disk_to_cart, mitsuba_brdf_draw.py:40-43
+        ox = x0; oy = x1;
+        pdf = pdf * oz;
+    } else {                                                        // brdf_measured_spherical.py:79-92
+        float st, ct, sp, cp;
+        sincosf(x0, &st, &ct);
+        sincosf(x1, &sp, &cp);
+        if (!(st > 0.00005f)) pdf = 0.0f;
+        if (P.epilogue == kEpiSpherical && !(ct > 0.0f)) pdf = 0.0f;
+        ox = cp * st; oy = sp * st; oz = ct;                        // sph_to_dir :31-34
+        pdf = pdf * inv_sin_clamped(ox, oy);                        // bsdf_myresult.py:81 (abs is a no-op on a sqrt)
+    }
+    P.out_dir[3 * i] = ox; P.out_dir[3 * i + 1] = oy; P.out_dir[3 * i + 2] = oz;
+    P.out_pdf[i] = pdf;
+}
+
+// Final masks / Jacobian for pdf() (tensor part of MyBSDF.pdf).
+__device__ __forceinline__ void store_pdf(const FlowParams& P, long long i, float pdf, float wiz,
+                                          float wox, float woy, float woz, float theta_o) {
+    if (P.epilogue == kEpiDisk) {                                   // brdf_measured_disk.py:122-124
+        pdf = (wiz > 0.0f && woz > 0.0f) ? pdf * woz : 0.0f;
+    } else if (P.epilogue == kEpiSpherical) {                       // brdf_measured_spherical.py:134-137
+        if (!(sinf(theta_o) > 0.00005f)) pdf = 0.0f;
+        pdf = (wiz > 0.0f && woz > 0.0f) ? pdf * inv_sin_clamped(wox, woy) : 0.0f;
+    } else if (P.epilogue == kEpiBsdf) {                            // bsdf_myresult.py:121-130
+        pdf = pdf * inv_sin_clamped(wox, woy);
+    }
+    P.out_pdf[i] = pdf;
+}
+
+int launch_simt(const FlowParams& P, cudaStream_t stream);
+int launch_tc(const FlowParams& P, cudaStream_t stream);
+int launch_mlp_forward_simt(long long n, const float* in, int in_dim, const unsigned char* flow, int H, int n_hidden,
+                            float* out, cudaStream_t stream);
+
+}  // namespace bsdfdiff

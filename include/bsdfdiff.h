@@ -1,0 +1,122 @@
+/* bsdfdiff.h -- C ABI of the B200-native neural BSDF sampler (libbsdfdiff.so).
+ *
+ * This is the drop-in boundary for the reference's hot path (fzy28/BSDF_diffusion_sampling @ f2b615c):
+ * everything the reference does between "a batch of incident directions arrives as a tensor" and
+ * "outgoing directions + pdf leave as tensors" is behind these entry points.  Plain pointers and
+ * sizes only; all data pointers are DEVICE pointers unless a parameter says "host"; every launch is
+ * enqueued on the given stream and the call returns without synchronising (CUDA-graph capturable,
+ * like tiny-cuda-nn's binding: tiny-cuda-nn/bindings/torch/tinycudann/bindings.cpp:95-96).
+ * Return value: 0 on success, a negative BSDFDIFF_E* code otherwise; never throws.
+ *
+ * Reference interfaces replaced (file:line in the reference checkout):
+ *   bsdfdiff_sample   <- network_sampling_disk       rendering/utils/mlp_brdf_sampling.py:17-51
+ *                        network_sampling_spherical  rendering/utils/mlp_brdf_sampling.py:106-140
+ *                        + tensor part of MyBSDF.sample: rendering/brdf_measured_disk.py:66-82,
+ *                          rendering/brdf_measured_spherical.py:76-92, rendering/bsdf_myresult.py:65-84
+ *   bsdfdiff_pdf      <- network_pdf_disk            rendering/utils/mlp_brdf_sampling.py:69-103
+ *                        network_pdf_spherical       rendering/utils/mlp_brdf_sampling.py:144-181
+ *                        + tensor part of MyBSDF.pdf: rendering/brdf_measured_disk.py:112-124,
+ *                          rendering/brdf_measured_spherical.py:122-137, rendering/bsdf_myresult.py:115-130
+ *   bsdfdiff_flow_forward <- rectify_stage.dosampling learning_repo_cleanup/disk_domain_sampling.py:93-110,
+ *                        learning_repo_cleanup/spherical_domain_sampling.py:147-166,
+ *                        learning_repo_cleanup/bsdf_correct_sampling.py:147-166 and
+ *                        network_sampling_disk_tiny  rendering/utils/mlp_brdf_sampling.py:54-68
+ *                        (the T-step loop around tinycudann.Network.forward,
+ *                        tiny-cuda-nn/bindings/torch/tinycudann/modules.py:176-192)
+ *   bsdfdiff_mlp_forward  <- tinycudann.Network(...)(x)  modules.py:176-192 /
+ *                        kernel_mlp_fused  tiny-cuda-nn/src/fully_fused_mlp.cu:499-557 (inference)
+ *   bsdfdiff_pack_flow / bsdfdiff_pack_flow_tcnn
+ *                     <- load_pytorch_model_to_tinycuda learning_repo_cleanup/utils/utils.py:13-23
+ *                        and the torch.load + load_state_dict at rendering/brdf_measured_disk.py:43-51
+ */
+#ifndef BSDFDIFF_H_
+#define BSDFDIFF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSDFDIFF_ABI_VERSION 1
+
+/* domains (state parameterisation of the flow) */
+#define BSDFDIFF_DISK       0   /* state = projected (x,y) on the unit disk; net input 25 = [x,y,alpha,PE5(wi)] */
+#define BSDFDIFF_SPHERICAL  1   /* state = (theta,phi); net input 26 = [theta,sin phi,cos phi,alpha,PE5(wi)]    */
+
+/* epilogues */
+#define BSDFDIFF_EPI_RAW        0   /* wi,wo are [n,2] domain coordinates; returns what mlp_brdf_sampling.py returns */
+#define BSDFDIFF_EPI_DISK       1   /* brdf_measured_disk.py plugin: wi/wo [n,3] local frame, out wo3 + pdf*cos(theta_o) */
+#define BSDFDIFF_EPI_SPHERICAL  2   /* brdf_measured_spherical.py plugin: wi/wo [n,3], sin/cos masks, pdf/sin(theta_o)   */
+#define BSDFDIFF_EPI_BSDF       3   /* bsdf_myresult.py plugin: as 2 without the cos mask, abs() in 1/sin                */
+
+/* arithmetic paths */
+#define BSDFDIFF_PREC_FP32  0   /* CUDA-core fp32 (parity path: matches the reference to ~1e-5)                 */
+#define BSDFDIFF_PREC_TC16  1   /* tcgen05: fp16 operands, fp32 TMEM accumulators (throughput path)             */
+
+/* error codes */
+#define BSDFDIFF_OK            0
+#define BSDFDIFF_EINVAL       -1   /* bad argument (null pointer, unsupported shape, T < 1, ...) */
+#define BSDFDIFF_EUNSUPPORTED -2   /* shape not supported by the requested precision path        */
+#define BSDFDIFF_ECUDA        -3   /* a CUDA runtime call failed (see bsdfdiff_last_cuda_error)   */
+#define BSDFDIFF_ENOTSM100    -4   /* device is not compute capability 10.x                       */
+
+#define BSDFDIFF_BASE_FLOATS 308   /* base net blob: W1[16x14] row-major, b1[16], Wo[4x16] row-major, bo[4] */
+
+int         bsdfdiff_abi_version(void);
+const char* bsdfdiff_error_string(int code);
+int         bsdfdiff_last_cuda_error(void);          /* cudaError_t of the last failure on this thread */
+
+/* ---- weight packing (host side; the blob is then copied to the device by the caller) ------------------------
+ * Flow net = bias-free MLP, layers given as row-major [rows,cols] fp32 matrices exactly as the checkpoints
+ * store them (nn.Linear.weight): W1 [H,in], W2..Wk [H,H], Wout [2,H];  in = 25 (disk) or 26 (spherical),
+ * H = 32 or 64.  The blob holds an fp32 image for the PREC_FP32 path and an fp16 shared-memory image
+ * (UMMA canonical K-major core-matrix layout) for the PREC_TC16 path.  The launch entry points take the
+ * device copy of the blob plus (hidden, n_hidden) so that no call ever reads device memory from the host. */
+size_t bsdfdiff_packed_flow_bytes(int in_dim, int hidden, int n_hidden);
+int    bsdfdiff_pack_flow(const float* const* layer_ptrs /*host*/, const int* rows, const int* cols, int n_layers,
+                          void* packed_out /*host, bsdfdiff_packed_flow_bytes()*/);
+/* Same, from the flat fp16/fp32 parameter vector of tinycudann.Network.params in the layout written by
+ * load_pytorch_model_to_tinycuda (first layer padded to in+16-in%16 columns, last to out+16-out%16 rows). */
+int    bsdfdiff_pack_flow_tcnn(const float* tcnn_params /*host, fp32 copy of .params*/, int in_dim, int out_dim,
+                               int hidden, int n_hidden, void* packed_out /*host*/);
+
+/* ---- sample: x0 ~ base(.|wi); T Euler steps of the flow; pdf = p_base(x0) / prod det(I + dD/dx / T) ---------
+ * wi:        [n,2] domain coords (EPI_RAW) or [n,3] local-frame directions (plugin epilogues)
+ * x0_replay: optional [n,2] externally supplied base sample (noise replay for parity); NULL = draw with
+ *            Philox4x32-10, key = seed, counter = (first_index + i, offset)  -> results do not depend on
+ *            how the batch is sharded across GPUs.
+ * out_dir:   [n,2] (EPI_RAW: x_T) or [n,3] (plugin: wo);  out_pdf: [n];  out_x0: optional [n,2].
+ * T >= 1; T == 0 together with flow_packed == NULL evaluates the base distribution alone
+ * (D_base.sample / D_base.log_prob, rendering/utils/model.py:387-398, 299-317). */
+int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
+                    const float* wi, const void* flow_packed, int hidden, int n_hidden,
+                    const float* base_params, const float* x0_replay, uint64_t seed, uint64_t offset, int64_t first_index,
+                    float* out_dir, float* out_pdf, float* out_x0, void* cuda_stream);
+
+/* ---- pdf: reverse flow from wo; pdf = p_base(x_T | wi) * prod det(I - dD/dx / T) ---------------------------- */
+int bsdfdiff_pdf(int precision, int domain, int epilogue, int T, int64_t n,
+                 const float* wo, const float* wi, const void* flow_packed, int hidden, int n_hidden,
+                 const float* base_params, float* out_pdf, void* cuda_stream);
+
+/* ---- forward-only flow (reflow "dosampling"): x_T = x0 + sum_t D(x_t, t/T | wi)/T, no pdf -------------------
+ * wi: [n_wi,2] domain coords; query i uses wi[i / wi_repeat] (repeat_interleave without materialising it).
+ * x0: [n,2] start state, or NULL to draw it from the base net (base_params required) with Philox;
+ * out_x0 (optional) receives the start state. */
+int bsdfdiff_flow_forward(int precision, int domain, int T, int64_t n, const float* wi, int64_t wi_repeat,
+                          const void* flow_packed, int hidden, int n_hidden, const float* base_params,
+                          const float* x0, uint64_t seed, uint64_t offset, int64_t first_index,
+                          float* out_x, float* out_x0, void* cuda_stream);
+
+/* ---- one MLP forward (tinycudann.Network.forward, inference): out[n,2] = MLP(in[n,in_dim]) ------------------ */
+int bsdfdiff_mlp_forward(int precision, int64_t n, const float* in, int in_dim, const void* flow_packed,
+                         int hidden, int n_hidden, float* out /*[n,2]*/, void* cuda_stream);
+
+/* Static facts about the tensor-core kernel for a given shape (for bench.py / DESIGN.md bookkeeping). */
+int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSDFDIFF_H_ */

@@ -1,0 +1,417 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200).  Everything goes through the C-ABI library via the
+package's public API; the CPU oracle (oracle/) is only the checker.
+
+Tolerances (stated up front):
+  fp32 CUDA-core path vs reference/oracle:  |d x| <= 2e-5 * max(1,|x|),  pdf rel err p99 <= 1e-4 (goldens: 2e-4,
+      the golden itself carries the reference's own fp32 rounding)
+  tc16 tensor-core path vs reference/oracle: |d x| median <= 5e-4, p99 <= 1e-2; pdf rel err median <= 5e-3,
+      p99 <= 5e-2; <= 0.1 % of queries may exceed 50 % rel err (near-singular step determinant) but must stay finite
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import BSDF_FILE, DISK_FILE, GOLDEN_FILES, SPH_FILE, golden_ids
+from oracle import bsdf_oracle as O
+from oracle import c_oracle as C
+
+pytestmark = pytest.mark.gpu
+
+PRECISIONS = ["fp32", "tc16"]
+
+
+@pytest.fixture(scope="module")
+def pkg(built_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return built_lib
+
+
+def rel(a, b):
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-6)
+
+
+def check_x(x, ref, prec):
+    err = np.abs(x - ref)
+    if prec == "fp32":
+        assert (err <= 2e-5 * np.maximum(1.0, np.abs(ref))).all(), f"max |dx| = {err.max()}"
+    else:
+        assert np.median(err) <= 5e-4, f"median |dx| = {np.median(err)}"
+        assert np.quantile(err, 0.99) <= 1e-2, f"p99 |dx| = {np.quantile(err, 0.99)}"
+
+
+def check_pdf(p, ref, prec, golden=False):
+    ok = np.isfinite(ref)
+    assert np.isfinite(p[ok]).mean() > 0.999
+    r = rel(p[ok], ref[ok])
+    r = r[np.isfinite(r)]
+    if prec == "fp32":
+        assert np.quantile(r, 0.99) <= (2e-4 if golden else 1e-4), f"p99 rel = {np.quantile(r, 0.99)}"
+        assert np.median(r) <= 2e-5
+    else:
+        assert np.median(r) <= 5e-3, f"median rel = {np.median(r)}"
+        assert np.quantile(r, 0.99) <= 5e-2, f"p99 rel = {np.quantile(r, 0.99)}"
+        assert (r > 0.5).mean() <= 1e-3
+
+
+def load(pkg, path, device="cuda"):
+    flow, base, z = O.load_material_npz(path)
+    pf = pkg.weights.pack_flow_layers(flow.layers, device)
+    pb = pkg.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, device)
+    return flow, base, z, pf, pb
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def kind_of(z):
+    if int(z["domain"]) == 0:
+        return "disk", 1
+    return ("bsdf", 3) if str(z["kind"]) == "bsdf" else ("spherical", 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# 1. golden vectors produced by the reference's own functions
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=golden_ids())
+def test_sample_golden(pkg, path, prec):
+    flow, base, z, pf, pb = load(pkg, path)
+    x, pdf, x0 = pkg.ops.sample(cu(z["wi"]), pf, pb, int(z["T"]), x0=cu(z["x0"]), precision=prec)
+    assert torch.equal(x0.cpu(), torch.from_numpy(z["x0"]))
+    check_x(x.cpu().numpy(), z["x"], prec)
+    check_pdf(pdf.cpu().numpy(), z["pdf_sample"], prec, golden=True)
+    if prec == "fp32":
+        assert np.array_equal(np.sign(pdf.cpu().numpy()), np.sign(z["pdf_sample"]))
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=golden_ids())
+def test_pdf_golden(pkg, path, prec):
+    flow, base, z, pf, pb = load(pkg, path)
+    p = pkg.ops.pdf(cu(z["wo_eval"]), cu(z["wi_eval"]), pf, pb, int(z["T"]), precision=prec)
+    check_pdf(p.cpu().numpy(), z["pdf_eval"], prec, golden=True)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("path", [DISK_FILE, SPH_FILE, BSDF_FILE], ids=["disk", "spherical", "bsdf"])
+def test_other_T_golden(pkg, path, prec):
+    flow, base, z, pf, pb = load(pkg, path)
+    n, T2 = z["x_t2"].shape[0], int(z["T2"])
+    x, pdf, _ = pkg.ops.sample(cu(z["wi"][:n]), pf, pb, T2, x0=cu(z["x0_t2"]), precision=prec)
+    check_x(x.cpu().numpy(), z["x_t2"], prec)
+    p = pkg.ops.pdf(cu(z["wo_eval"][:n]), cu(z["wi_eval"][:n]), pf, pb, T2, precision=prec)
+    r = rel(p.cpu().numpy(), z["pdf_eval_t2"])
+    assert np.quantile(r, 0.95) <= (2e-4 if prec == "fp32" else 5e-2)
+
+
+def test_reference_named_entry_points(pkg):
+    """network_sampling_* / network_pdf_* with nn.Module arguments, as the reference's plugins call them."""
+    m = pkg.model
+    for path, T in ((DISK_FILE, 4), (SPH_FILE, 8)):
+        flow, base, z = O.load_material_npz(path)
+        if T == 4:
+            D = m.NN_cond_pos_simpler(input_dim=5, output_dim=2, N_NEURONS=32, POSITIONAL_ENCODING_BASIS_NUM=5)
+            B = m.NN_cond_pretrain_disk_one(input_dim=2, N_NEURONS=16, POSITIONAL_ENCODING_BASIS_NUM=3)
+            fs, fp = pkg.network_sampling_disk, pkg.network_pdf_disk
+        else:
+            D = m.NN_cond_pos(input_dim=6, output_dim=2, N_NEURONS=32, POSITIONAL_ENCODING_BASIS_NUM=5)
+            B = m.NN_cond_pretrain_spherical_one(input_dim=2, N_NEURONS=16)
+            fs, fp = pkg.network_sampling_spherical, pkg.network_pdf_spherical
+        D.load_state_dict({k: torch.from_numpy(w) for k, w in zip(D.state_dict().keys(), flow.layers)})
+        B.load_state_dict({"linear1.weight": torch.from_numpy(base.w1), "linear1.bias": torch.from_numpy(base.b1),
+                           "output.weight": torch.from_numpy(base.wo), "output.bias": torch.from_numpy(base.bo)})
+        D, B = D.cuda(), B.cuda()
+        wi = cu(z["wi"])
+        x, pdf = fs(B, D, wi, x0=cu(z["x0"]), precision="fp32")
+        assert x.shape == (wi.shape[0], 2) and pdf.shape == (wi.shape[0],) and not x.requires_grad
+        check_x(x.cpu().numpy(), z["x"], "fp32")
+        p = fp(B, D, torch.from_numpy(z["wo_eval"]), cu(z["wi_eval"]), precision="fp32")   # omega_o on the CPU, like :71
+        check_pdf(p.cpu().numpy(), z["pdf_eval"], "fp32", golden=True)
+        # default path: torch's generator drives Philox -> manual_seed reproduces, different seeds differ
+        torch.manual_seed(7)
+        a, _ = fs(B, D, wi, precision="fp32")
+        torch.manual_seed(7)
+        b, _ = fs(B, D, wi, precision="fp32")
+        c, _ = fs(B, D, wi, precision="fp32")
+        assert torch.equal(a, b) and not torch.equal(a, c)
+        # base net alone through the library (T = 0)
+        lp = B.log_prob(cu(z["x0"]), wi).cpu().numpy()
+        want = (O.base_logprob_disk if T == 4 else O.base_logprob_spherical)(base, z["x0"], z["wi"])
+        assert np.quantile(np.abs(lp - want), 0.99) <= 1e-4 * (1 + np.abs(want).max())
+        assert B.sample(wi).shape == (wi.shape[0], 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# 2. larger seeded batches against the oracle, plugin epilogues included
+# ------------------------------------------------------------------------------------------------
+def random_dirs(n, rng, full_sphere=False):
+    w = rng.normal(size=(n, 3)).astype(np.float32)
+    if not full_sphere:
+        w[:, 2] = np.abs(w[:, 2]) + 0.02
+    return (w / np.linalg.norm(w, axis=1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("path", [DISK_FILE, SPH_FILE, BSDF_FILE], ids=["disk", "spherical", "bsdf"])
+def test_plugin_sample_and_pdf_vs_oracle(pkg, path, prec):
+    flow, base, z, pf, pb = load(pkg, path)
+    kind, epi = kind_of(z)
+    T = int(z["T"])
+    n = 200_003                                                     # ragged last tile
+    rng = np.random.default_rng(11)
+    wi3 = random_dirs(n, rng, full_sphere=(kind == "bsdf"))
+    s = pkg.plugins.NeuralBSDFSampler(kind, pf, pb, precision=prec)
+    wo, pdf, x0 = pkg.ops.sample(cu(wi3), pf, pb, T, epilogue=epi, seed=123, offset=0, precision=prec)
+    wo_ref, pdf_ref = C.sample(flow, base, wi3, T, x0.cpu().numpy(), epilogue=epi)
+    wo, pdf = wo.cpu().numpy(), pdf.cpu().numpy()
+    err = np.abs(wo - wo_ref)
+    if prec == "fp32":
+        assert np.quantile(err, 0.999) <= 2e-5 and err.max() <= 1e-3
+    else:
+        assert np.median(err) <= 5e-4 and np.quantile(err, 0.99) <= 1e-2
+    zero_ref, zero = (pdf_ref == 0), (pdf == 0)
+    assert (zero_ref == zero).mean() >= (0.9999 if prec == "fp32" else 0.995)      # validity / sin / cos masks
+    both = ~zero_ref & ~zero
+    check_pdf(pdf[both], pdf_ref[both], prec)
+    # pdf() at the sampled directions (plus mask cases: flip some wo below the horizon)
+    wo_q = wo_ref.copy()
+    wo_q[::7, 2] *= -1.0
+    p = s.pdf(cu(wi3), cu(wo_q)).cpu().numpy()
+    p_ref = C.pdf(flow, base, wo_q, wi3, T, epilogue=epi)
+    assert ((p_ref == 0) == (p == 0)).mean() >= (0.9999 if prec == "fp32" else 0.995)
+    both = (p_ref != 0) & (p != 0)
+    check_pdf(p[both], p_ref[both], prec)
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_sample_pdf_consistency_at_large_T(pkg, prec):
+    """Size-independent property: forward and reverse Euler are mutually inverse as T grows, so
+    pdf(sample().x) -> sample().pdf.  (At the plugins' T=4/8 they differ by design)"""
+    flow, base, z, pf, pb = load(pkg, DISK_FILE)
+    wi = cu(O.stratified_wi_disk(64))
+    x, pdf_s, _ = pkg.ops.sample(wi, pf, pb, 256, seed=5, precision=prec)
+    pdf_e = pkg.ops.pdf(x, wi, pf, pb, 256, precision=prec)
+    r = rel(pdf_e.cpu().numpy(), pdf_s.cpu().numpy())
+    assert np.median(r) <= 2e-2
+
+
+# ------------------------------------------------------------------------------------------------
+# 3. Philox noise: determinism, shard invariance, distribution
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_philox_shard_invariance_and_determinism(pkg, prec):
+    flow, base, z, pf, pb = load(pkg, SPH_FILE)
+    n = 100_001
+    rng = np.random.default_rng(2)
+    wi = cu(np.stack([rng.uniform(0, np.pi / 2, n), rng.uniform(-np.pi, np.pi, n)], 1).astype(np.float32))
+    a = pkg.ops.sample(wi, pf, pb, 8, seed=99, offset=4, precision=prec)
+    b = pkg.ops.sample(wi, pf, pb, 8, seed=99, offset=4, precision=prec)
+    for u, v in zip(a, b):
+        assert torch.equal(u, v)
+    cut = 33_333
+    lo = pkg.ops.sample(wi[:cut], pf, pb, 8, seed=99, offset=4, first_index=0, precision=prec)
+    hi = pkg.ops.sample(wi[cut:], pf, pb, 8, seed=99, offset=4, first_index=cut, precision=prec)
+    for u, l, h in zip(a, lo, hi):
+        assert torch.equal(u, torch.cat([l, h], 0)), "results must not depend on how the batch is sharded"
+    c = pkg.ops.sample(wi, pf, pb, 8, seed=100, offset=4, precision=prec)
+    assert not torch.equal(a[2], c[2])
+
+
+def test_base_sampler_distribution(pkg):
+    """x0 drawn in-kernel follows the base distribution: standardised disk Gaussian ~ N(0,I);
+    spherical phi0 ~ vonMises(mu, kappa) (two-sample KS against numpy's sampler)."""
+    from scipy import stats
+    flow, base, z, pf, pb = load(pkg, DISK_FILE)
+    n = 400_000
+    wi_np = np.tile(np.array([[0.3, -0.2]], np.float32), (n, 1))
+    _, _, x0 = pkg.ops.sample(cu(wi_np), pf, pb, 1, seed=1, precision="fp32")
+    p = O.base_forward(base, wi_np[:1])[0]
+    e = (x0.cpu().numpy() - p[:2]) / np.exp(p[2:])
+    assert abs(e.mean()) < 5e-3 and np.abs(e.std(0) - 1).max() < 5e-3
+    assert abs(np.corrcoef(e.T)[0, 1]) < 5e-3
+    assert stats.kstest(e[:50_000, 0], "norm").pvalue > 1e-3
+
+    flow, base, z, pf, pb = load(pkg, BSDF_FILE)
+    for wi_fixed in ([0.6, 0.9], [2.2, -2.0]):
+        wi_np = np.tile(np.array([wi_fixed], np.float32), (n, 1))
+        _, _, x0 = pkg.ops.sample(cu(wi_np), pf, pb, 1, seed=3, precision="fp32")
+        loc, ls, mu, kappa = (a[0] for a in O.base_params_spherical(base, wi_np[:1]))
+        x0 = x0.cpu().numpy()
+        th = (x0[:, 0] - loc) / (np.exp(ls) + 1e-3)
+        assert abs(th.mean()) < 5e-3 and abs(th.std() - 1) < 5e-3
+        ref = np.random.default_rng(0).vonmises(float(mu), float(kappa), 50_000)
+        ref = (ref + np.pi) % (2 * np.pi) - np.pi
+        assert x0[:, 1].min() >= -np.pi - 1e-5 and x0[:, 1].max() <= np.pi + 1e-5
+        assert stats.ks_2samp(x0[:50_000, 1], ref).pvalue > 1e-3, f"von Mises mismatch (kappa={kappa})"
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_chi_square_two_sample_vs_oracle(pkg, prec):
+    """64K outgoing samples for one fixed wi (BASELINE config 1): histogram of the kernel's own Philox
+    samples vs the oracle pushed through INDEPENDENT base samples -> two-sample chi-square."""
+    from scipy import stats
+    flow, base, z, pf, pb = load(pkg, DISK_FILE)
+    n = 65_536
+    wi_np = np.tile(np.array([[0.3, -0.2]], np.float32), (n, 1))
+    x, _, _ = pkg.ops.sample(cu(wi_np), pf, pb, 4, seed=2024, precision=prec)
+    x = x.cpu().numpy()
+    x_ref, _, _ = O.sample_disk(flow, base, wi_np, 4, rng=np.random.default_rng(77))
+    lo, hi = np.quantile(x_ref, 0.001, axis=0), np.quantile(x_ref, 0.999, axis=0)
+    bins = [np.linspace(lo[0], hi[0], 13), np.linspace(lo[1], hi[1], 13)]
+    ha, _, _ = np.histogram2d(x[:, 0], x[:, 1], bins)
+    hb, _, _ = np.histogram2d(x_ref[:, 0], x_ref[:, 1], bins)
+    keep = (ha + hb) >= 20
+    chi2 = (((ha - hb) ** 2) / (ha + hb))[keep].sum()
+    pval = stats.chi2.sf(chi2, keep.sum() - 1)
+    assert pval > 1e-3, f"chi2={chi2:.1f} dof={keep.sum() - 1} p={pval:.2e}"
+
+
+# ------------------------------------------------------------------------------------------------
+# 4. edge cases
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_edge_sizes_and_layouts(pkg, prec):
+    flow, base, z, pf, pb = load(pkg, DISK_FILE)
+    wi_all, x0_all = z["wi"], z["x0"]
+    ref_x, ref_pdf = C.sample(flow, base, wi_all, 4, x0_all)
+    for n in (0, 1, 31, 127, 128, 129, 383, 385, 2176):
+        x, pdf, _ = pkg.ops.sample(cu(wi_all[:n]), pf, pb, 4, x0=cu(x0_all[:n]), precision=prec)
+        assert x.shape == (n, 2) and pdf.shape == (n,)
+        if n:
+            check_x(x.cpu().numpy(), ref_x[:n], prec) if n > 100 else None
+            assert np.isfinite(x.cpu().numpy()).all()
+    # non-contiguous / float64 inputs are accepted (converted), like tensors arriving from Dr.Jit
+    wi_nc = cu(np.concatenate([wi_all, wi_all], 1))[:, :2].double()
+    x, pdf, _ = pkg.ops.sample(wi_nc, pf, pb, 4, x0=cu(x0_all), precision=prec)
+    check_x(x.cpu().numpy(), ref_x, prec)
+    # NaN / inf conditioning must not crash or poison neighbours
+    wi_bad = wi_all.copy()
+    wi_bad[5] = np.nan
+    wi_bad[9] = np.inf
+    x, pdf, _ = pkg.ops.sample(cu(wi_bad), pf, pb, 4, x0=cu(x0_all), precision=prec)
+    xn = x.cpu().numpy()
+    good = np.ones(len(wi_bad), bool)
+    good[[5, 9]] = False
+    if prec == "fp32":
+        check_x(xn[good], ref_x[good], prec)
+    else:
+        # a tensor-core tile shares nothing between rows either
+        check_x(xn[good], ref_x[good], prec)
+    with pytest.raises(ValueError):
+        pkg.ops.sample(cu(wi_all), pf, pb, 0, precision=prec)
+    with pytest.raises(ValueError):
+        pkg.ops.pdf(cu(wi_all[:5]), cu(wi_all), pf, pb, 4, precision=prec)
+    with pytest.raises(ValueError):
+        pkg.plugins.NeuralBSDFSampler("spherical", pf, pb)           # disk net in a spherical plugin
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_cuda_graph_capture(pkg, prec):
+    """The entry points never synchronise or allocate outside torch's allocator -> capturable."""
+    flow, base, z, pf, pb = load(pkg, SPH_FILE)
+    wi, x0 = cu(z["wi"]), cu(z["x0"])
+    pkg.ops.sample(wi, pf, pb, 8, x0=x0, precision=prec)            # warm-up (attribute setup)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = pkg.ops.sample(wi, pf, pb, 8, x0=x0, precision=prec)
+    g.replay()
+    torch.cuda.synchronize()
+    check_x(out[0].cpu().numpy(), z["x"], prec)
+
+
+# ------------------------------------------------------------------------------------------------
+# 5. reflow (dosampling) and the tinycudann.Network shim
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("path", [DISK_FILE, SPH_FILE], ids=["disk_w32", "spherical_w64"])
+def test_reflow_forward_vs_reference(pkg, path, prec):
+    flow, base, z = O.load_material_npz(path)
+    if "reflow_w0" in z:
+        flow = O.FlowWeights([z[f"reflow_w{i}"] for i in range(int(z["n_reflow_layers"]))])
+    pf = pkg.weights.pack_flow_layers(flow.layers, "cuda")
+    T = int(z["reflow_T"])
+    x, x0 = pkg.ops.flow_forward(cu(z["reflow_wi"]), pf, T, x0=cu(z["reflow_x0"]), precision=prec)
+    err = np.abs(x.cpu().numpy() - z["reflow_x"])
+    if prec == "fp32":
+        assert err.max() <= 3e-5
+    else:   # tiny-cuda-nn's own fp16 bar is rtol=atol=1e-2 for ONE forward (tiny-cuda-nn/tmp.py:59)
+        assert np.quantile(err, 0.99) <= 1e-2
+    # long T at the reference's setting (256 disk / 128 spherical) against the C oracle
+    T_long = 256 if flow.domain == O.DISK else 128
+    x, _ = pkg.ops.flow_forward(cu(z["reflow_wi"]), pf, T_long, x0=cu(z["reflow_x0"]), precision=prec)
+    ref = C.reflow(flow, z["reflow_x0"], z["reflow_wi"], T_long)
+    err = np.abs(x.cpu().numpy() - ref)
+    assert err.max() <= 1e-4 if prec == "fp32" else np.quantile(err, 0.99) <= 2e-2
+
+
+def test_dosampling_and_network_shim(pkg):
+    flow, base, z = O.load_material_npz(DISK_FILE)
+    m, r = pkg.model, pkg.reflow
+    B = m.NN_cond_pretrain_disk_one(input_dim=2, N_NEURONS=16, POSITIONAL_ENCODING_BASIS_NUM=3)
+    B.load_state_dict({"linear1.weight": torch.from_numpy(base.w1), "linear1.bias": torch.from_numpy(base.b1),
+                       "output.weight": torch.from_numpy(base.wo), "output.bias": torch.from_numpy(base.bo)})
+    net = r.Network(25, 2, {"otype": "FullyFusedMLP", "activation": "SiLU", "output_activation": "None",
+                            "n_neurons": 32, "n_hidden_layers": 3})
+    r.load_pytorch_model_to_tinycuda(net, {f"l{i}": torch.from_numpy(w) for i, w in enumerate(flow.layers)}, 25, 2)
+    net, B = net.cuda(), B.cuda()
+    # one forward: fp16 weights, [N,25] f32 -> [N,2] f16, within tcnn's rtol=atol=1e-2 of the fp32 module
+    rng = np.random.default_rng(0)
+    wi = O.stratified_wi_disk(8)
+    inp = np.concatenate([rng.uniform(-1, 1, (64, 2)).astype(np.float32), np.full((64, 1), 0.25, np.float32),
+                          O.positional_encoding(wi, 5)], 1)
+    out = net(cu(inp))
+    assert out.dtype == torch.float16 and out.shape == (64, 2)
+    h = inp
+    for w in flow.layers[:-1]:
+        h = O.silu(h @ w.T)
+    want = h @ flow.layers[-1].T
+    assert np.allclose(out.float().cpu().numpy(), want, rtol=1e-2, atol=1e-2)
+    # dosampling: N = batchsize * len(omega_i), x_target_y is repeat_interleave'd, x_base ~ base
+    omega = cu(wi[:16])
+    x1, xb, y = r.dosampling(1024, omega, 32, B, net, seed=11, precision="fp32")
+    assert x1.shape == xb.shape == y.shape == (16 * 1024, 2)
+    assert torch.equal(y, omega.repeat_interleave(1024, 0))
+    layers16 = O.FlowWeights([w.astype(np.float16).astype(np.float32) for w in flow.layers])
+    ref = C.reflow(layers16, xb.cpu().numpy(), y.cpu().numpy(), 32)
+    assert np.abs(x1.cpu().numpy() - ref).max() <= 5e-5
+    # network_sampling_disk_tiny keeps the reference signature (pdf == 1)
+    xt, ones = pkg.network_sampling_disk_tiny(xb[:256], net, cu(O.positional_encoding(y.cpu().numpy()[:256], 5)), T=4)
+    assert xt.shape == (256, 2) and torch.equal(ones, torch.ones(256, device="cuda"))
+    ref = C.reflow(layers16, xb[:256].cpu().numpy(), y[:256].cpu().numpy(), 4)
+    assert np.abs(xt.cpu().numpy() - ref).max() <= 2e-2            # fp16 output rounding each step, like tcnn
+
+
+# ------------------------------------------------------------------------------------------------
+# 6. full BASELINE size: 16M queries, size-independent properties
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", PRECISIONS)
+def test_16M_queries_properties(pkg, prec):
+    flow, base, z, pf, pb = load(pkg, DISK_FILE)
+    n_side = 4096
+    n = n_side * n_side                                               # 16,777,216
+    wi = cu(O.stratified_wi_disk(n_side))
+    s = pkg.plugins.NeuralBSDFSampler("disk", pf, pb, precision=prec)
+    wi3 = torch.cat([wi, torch.sqrt(torch.clamp(1 - (wi * wi).sum(1, keepdim=True), min=0))], 1).contiguous()
+    wo, pdf = s.sample(wi3, seed=42)
+    # (a) unit directions, valid hemisphere, finite non-negative-or-masked pdfs
+    nrm = (wo * wo).sum(1)
+    assert torch.allclose(nrm, torch.ones_like(nrm), atol=1e-5)
+    assert (wo[:, 2] >= 0).all() and torch.isfinite(pdf).all()
+    # (b) shard invariance at full size: two halves with first_index reproduce the whole bit-for-bit
+    half = n // 2
+    wo_a, pdf_a = s.sample(wi3[:half], seed=42, first_index=0)
+    wo_b, pdf_b = s.sample(wi3[half:], seed=42, first_index=half)
+    assert torch.equal(wo, torch.cat([wo_a, wo_b])) and torch.equal(pdf, torch.cat([pdf_a, pdf_b]))
+    # (c) a strided sample of the 16M agrees with the oracle (replaying the kernel's own x0)
+    idx = torch.arange(0, n, 4099, device="cuda")
+    _, _, x0 = pkg.ops.sample(wi3[idx], pf, pb, 4, epilogue=1, seed=42, precision=prec)   # different indices -> new x0
+    wo_s, pdf_s, _ = pkg.ops.sample(wi3[idx], pf, pb, 4, epilogue=1, x0=x0, precision=prec)
+    wo_r, pdf_r = C.sample(flow, base, wi3[idx].cpu().numpy(), 4, x0.cpu().numpy(), epilogue=1)
+    err = np.abs(wo_s.cpu().numpy() - wo_r)
+    assert np.quantile(err, 0.99) <= (2e-5 if prec == "fp32" else 1e-2)
+    # (d) importance-sampling sanity: E[1/pdf_xy] over valid samples ~ area of the support (<= pi)
+    ok = pdf > 0
+    area = (wo[ok, 2] / pdf[ok]).double().sum().item() / n           # pdf_omega = pdf_xy * cos  ->  1/pdf_xy = cos/pdf_omega
+    assert 0.5 < area < 1.15 * np.pi

@@ -1,0 +1,176 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/bsdfdiff.h declares, the host-side
+packer produces the documented layouts, argument validation / error behaviour, and the sharding logic
+(world_size-2 gloo).  No compute call is made without a GPU."""
+import ctypes
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import BSDF_FILE, DISK_FILE, GOLDEN_FILES, ROOT
+from oracle import bsdf_oracle as O
+
+
+def test_every_declared_symbol_is_exported(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "bsdfdiff.h")).read()
+    declared = set(re.findall(r"\b(bsdfdiff_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 11
+    lib = ctypes.CDLL(built_lib._lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/bsdfdiff.h but not exported"
+    assert set(built_lib._lib.EXPORTS) == declared
+    assert built_lib._lib.lib.bsdfdiff_abi_version() == 1
+    assert built_lib._lib.lib.bsdfdiff_error_string(-2).decode().startswith("shape not supported")
+
+
+def _unpack_header(blob):
+    import struct
+    magic, in_dim, H, nh, dom, off32, n32, off16, n16, total, off_aux, n_aux = struct.unpack("<I4i7I", blob[:48])
+    return dict(magic=magic, in_dim=in_dim, H=H, nh=nh, dom=dom, off32=off32, n32=n32, off16=off16, n16=n16,
+                total=total, off_aux=off_aux, n_aux=n_aux)
+
+
+@pytest.mark.parametrize("path", [DISK_FILE, BSDF_FILE])
+def test_pack_flow_layout(built_lib, path):
+    """fp32 image is the per-layer transpose; fp16 image is the UMMA K-major core-matrix layout with the
+    hidden layers pre-scaled by 0.5 and the output layer padded to 16 rows."""
+    flow, base, z = O.load_material_npz(path)
+    packed = built_lib.weights.pack_flow_layers(flow.layers, device="cpu")
+    blob = packed.blob.numpy().tobytes()
+    h = _unpack_header(blob)
+    H, in_dim, nh = flow.layers[0].shape[0], flow.in_dim, len(flow.layers) - 1
+    assert (h["magic"], h["in_dim"], h["H"], h["nh"]) == (0xB5DFD1F0, in_dim, H, nh)
+    assert h["total"] == len(blob) == built_lib._lib.lib.bsdfdiff_packed_flow_bytes(in_dim, H, nh)
+    f32 = np.frombuffer(blob, np.float32, h["n32"] // 4, h["off32"])
+    off = 0
+    for w in flow.layers:
+        assert np.array_equal(f32[off: off + w.size].reshape(w.shape[1], w.shape[0]), w.T)
+        off += w.size
+    f16 = np.frombuffer(blob, np.float16, h["n16"] // 2, h["off16"])
+
+    def at(img, n, k, N):
+        return img[((k // 8) * (N // 8) + n // 8) * 64 + (n % 8) * 8 + k % 8]
+
+    w1 = flow.layers[0]
+    img = f16[: H * 32]
+    n_state = 3 if in_dim == 25 else 4
+    for n in (0, 7, 13, H - 1):
+        for k in range(32):
+            src = k if k < in_dim else (k - in_dim if k - in_dim < n_state else None)
+            want = np.float16(0.5 * w1[n, src]) if src is not None else np.float16(0)
+            assert at(img, n, k, H) == want
+    img = f16[H * 32: H * 32 + H * H]
+    assert at(img, 5, 9, H) == np.float16(0.5 * flow.layers[1][5, 9])
+    img = f16[H * 32 + (nh - 1) * H * H:]
+    assert at(img, 1, 17, 16) == np.float16(flow.layers[-1][1, 17]) and at(img, 2, 3, 16) == 0
+    aux = np.frombuffer(blob, np.float32, h["n_aux"] // 4, h["off_aux"])
+    assert np.array_equal(aux[:H], (0.5 * w1[:, 0]).astype(np.float16).astype(np.float32))
+
+
+def test_pack_flow_tcnn_equals_pack_from_layers(built_lib):
+    flow, _, _ = O.load_material_npz(DISK_FILE)
+    layers16 = [w.astype(np.float16).astype(np.float32) for w in flow.layers]
+    a = built_lib.weights.pack_flow_layers(layers16, device="cpu").blob
+    params = O.pack_tcnn_params(flow.layers, flow.in_dim, 2).astype(np.float32)
+    b = built_lib.weights.pack_flow_tcnn(params, flow.in_dim, 2, 32, len(flow.layers) - 1, device="cpu").blob
+    assert torch.equal(a, b)
+
+
+def test_argument_validation_without_gpu(built_lib):
+    L = built_lib._lib
+    assert L.lib.bsdfdiff_packed_flow_bytes(25, 48, 3) == 0          # hidden must be 32 | 64
+    assert L.lib.bsdfdiff_packed_flow_bytes(40, 32, 3) == 0          # in_dim <= 32
+    with pytest.raises(L.BsdfDiffError):
+        built_lib.weights.pack_flow_layers([np.zeros((48, 25), np.float32), np.zeros((2, 48), np.float32)], "cpu")
+    with pytest.raises(L.BsdfDiffError):
+        built_lib.weights.pack_base_arrays(np.zeros((16, 14)), np.zeros(16), np.zeros((4, 16)), np.zeros(3), "cpu")
+    # invalid arguments are rejected before any CUDA call
+    assert L.lib.bsdfdiff_sample(0, 0, 0, 4, 16, None, None, 32, 3, None, None, 0, 0, 0, None, None, None, None) == -1
+    assert L.lib.bsdfdiff_sample(0, 0, 2, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, None, None) == -1  # sph epilogue on disk
+    assert L.lib.bsdfdiff_pdf(0, 1, 0, -1, 16, 1, 1, 1, 32, 4, 1, 1, None) == -1
+    # CPU tensors raise: there is no CPU path
+    flow, base, z = O.load_material_npz(DISK_FILE)
+    pf = built_lib.weights.pack_flow_layers(flow.layers, "cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        built_lib.ops.sample(torch.zeros(4, 2), pf, torch.zeros(308), 4, x0=torch.zeros(4, 2))
+
+
+def test_model_classes_load_reference_state_dict_keys(built_lib):
+    m = built_lib.model
+    flow, base, z = O.load_material_npz(DISK_FILE)
+    net = m.NN_cond_pos_simpler(input_dim=5, output_dim=2, N_NEURONS=32, POSITIONAL_ENCODING_BASIS_NUM=5)
+    assert list(net.state_dict().keys()) == ["linear1.weight", "linear2.weight", "linear3.weight", "output.weight"]
+    net.load_state_dict({k: torch.from_numpy(w) for k, w in zip(net.state_dict().keys(), flow.layers)})
+    sph = m.NN_cond_pos(input_dim=6, output_dim=2, N_NEURONS=32, POSITIONAL_ENCODING_BASIS_NUM=5)
+    assert sph.linear1.weight.shape == (32, 26) and hasattr(sph, "linear4") and not hasattr(sph, "linear5")
+    cx = m.NN_cond_pos_spherical_complicate(input_dim=6, output_dim=2, N_NEURONS=64, POSITIONAL_ENCODING_BASIS_NUM=5)
+    assert cx.linear6.weight.shape == (64, 64)
+    b = m.NN_cond_pretrain_disk_one(input_dim=2, N_NEURONS=16, POSITIONAL_ENCODING_BASIS_NUM=3)
+    assert b.linear1.weight.shape == (16, 14) and b.output.weight.shape == (4, 16)
+    packed = built_lib.weights.packed_flow_of(net, "cpu")
+    assert built_lib.weights.packed_flow_of(net, "cpu") is packed                    # cached
+    with torch.no_grad():
+        net.linear1.weight.mul_(2.0)
+    assert built_lib.weights.packed_flow_of(net, "cpu") is not packed                # invalidated by _version
+    pe = m.positional_encoding_1(torch.tensor([[0.3, -0.2]]), 5)
+    assert np.allclose(pe.numpy(), O.positional_encoding(np.array([[0.3, -0.2]], np.float32), 5), atol=1e-6)
+
+
+def test_tcnn_network_shim_layout(built_lib):
+    r = built_lib.reflow
+    net = r.Network(25, 2, {"otype": "FullyFusedMLP", "activation": "SiLU", "output_activation": "None",
+                            "n_neurons": 32, "n_hidden_layers": 3})
+    assert net.params.numel() == 32 * 32 + 2 * 1024 + 16 * 32
+    flow, _, _ = O.load_material_npz(DISK_FILE)
+    sd = {f"l{i}": torch.from_numpy(w) for i, w in enumerate(flow.layers)}
+    r.load_pytorch_model_to_tinycuda(net, sd, 25, 2)
+    want = O.pack_tcnn_params(flow.layers, 25, 2).astype(np.float32)
+    assert np.array_equal(net.params.detach().numpy(), want)
+    with pytest.raises(RuntimeError):
+        r.Network(25, 2, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
+                          "n_neurons": 32, "n_hidden_layers": 3})
+
+
+def test_shard_range_partitions(built_lib):
+    s = built_lib.sharding
+    for n in (0, 1, 7, 16, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [s.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    from bsdf_diffusion_sampling_b200 import sharding
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    full = torch.arange(n * 3, dtype=torch.float32).reshape(n, 3)
+    local = sharding.shard_rows(full, rank, world) * 2.0            # stand-in for the per-shard kernel
+    out = sharding.gather_rows(local, n)
+    ok = torch.equal(out, full * 2.0)
+    ss = sharding.ShardedSampler(sampler=None)
+    q.put((rank, ok, ss.local_range(n), ss.world))
+    dist.destroy_process_group()
+
+
+def test_gather_rows_gloo_world2(built_lib):
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n = 1001                                                        # ragged: 501 + 500
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert [r[1] for r in res] == [True, True]
+    assert res[0][2] == (0, 501) and res[1][2] == (501, 1001) and res[0][3] == 2
