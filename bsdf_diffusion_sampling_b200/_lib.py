@@ -15,12 +15,13 @@ LIB_PATH = os.path.join(HERE, "libbsdfdiff.so")
 # constants mirrored from include/bsdfdiff.h
 DISK, SPHERICAL = 0, 1
 EPI_RAW, EPI_DISK, EPI_SPHERICAL, EPI_BSDF = 0, 1, 2, 3
-PREC_FP32, PREC_TC16 = 0, 1
+PREC_FP32, PREC_TC16, PREC_TC16_EXP = 0, 1, 2
 BASE_FLOATS = 308
 ABI_VERSION = 1
 
 EXPORTS = [
-    "bsdfdiff_abi_version", "bsdfdiff_error_string", "bsdfdiff_last_cuda_error", "bsdfdiff_device_info",
+    "bsdfdiff_abi_version", "bsdfdiff_error_string", "bsdfdiff_last_cuda_error", "bsdfdiff_debug_timeout_flag",
+    "bsdfdiff_device_info",
     "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn",
     "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
 ]

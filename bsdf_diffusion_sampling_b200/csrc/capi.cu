@@ -30,6 +30,8 @@ extern "C" const char* bsdfdiff_error_string(int code) {
 
 extern "C" int bsdfdiff_last_cuda_error(void) { return g_last_cuda_error; }
 
+extern "C" int bsdfdiff_debug_timeout_flag(void) { return (int)tc_timeout_flag(); }
+
 extern "C" int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail_cuda();
@@ -68,12 +70,25 @@ static inline size_t umma_kmajor_index(int n, int k, int N) {
 
 // Column map of the tensor-core first layer (K = 32): hi parts, PE5(wi), then the lo parts of the
 // fp32 state so the fp16 A operand carries the state to ~2^-22 (see flow_tc.cu).
+//   k = 0..7  : the per-step state inputs, hi then lo fp16 parts (A columns 0..3, rewritten every step)
+//               disk      [x0_hi, x1_hi, a_hi, a_lo, x0_lo, x1_lo, 0, 0]
+//               spherical [th_hi, sin_hi, cos_hi, a_hi, th_lo, sin_lo, cos_lo, a_lo]
+//   k = 8..29 : PE5(wi) (22 values, constant over the T steps; A columns 4..14 written once per tile)
+//   k = 30,31 : zero
+// Nets that are not one of the two sampler shapes (generic tcnn MLPs) use the identity map.
 static void tc_layer1_source_columns(int domain, int in_dim, int src[32]) {
     for (int k = 0; k < 32; ++k) src[k] = -1;
-    for (int k = 0; k < in_dim; ++k) src[k] = k;
-    const int n_state = (domain == kDisk) ? 3 : 4;                 // x0,x1,alpha | theta,sin,cos,alpha
-    if (in_dim + n_state <= 32)
-        for (int s = 0; s < n_state; ++s) src[in_dim + s] = s;
+    if (in_dim == 25 && domain == kDisk) {
+        const int st[8] = {0, 1, 2, 2, 0, 1, -1, -1};
+        for (int k = 0; k < 8; ++k) src[k] = st[k];
+        for (int i = 0; i < kPE5; ++i) src[8 + i] = 3 + i;
+    } else if (in_dim == 26 && domain == kSpherical) {
+        const int st[8] = {0, 1, 2, 3, 0, 1, 2, 3};
+        for (int k = 0; k < 8; ++k) src[k] = st[k];
+        for (int i = 0; i < kPE5; ++i) src[8 + i] = 4 + i;
+    } else {
+        for (int k = 0; k < in_dim; ++k) src[k] = k;
+    }
 }
 
 static int pack_from_layers(const std::vector<const float*>& Ws, const std::vector<int>& rows,
@@ -183,7 +198,7 @@ extern "C" int bsdfdiff_pack_flow_tcnn(const float* p, int in_dim, int out_dim, 
 static int dispatch(int precision, const FlowParams& P, cudaStream_t stream) {
     int rc;
     if (precision == BSDFDIFF_PREC_FP32 || P.T == 0) rc = launch_simt(P, stream);
-    else if (precision == BSDFDIFF_PREC_TC16) rc = launch_tc(P, stream);
+    else if (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP) rc = launch_tc(P, stream, precision);
     else return BSDFDIFF_EINVAL;
     if (rc == -3) return fail_cuda();
     return rc;

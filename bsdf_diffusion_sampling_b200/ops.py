@@ -14,9 +14,10 @@ from typing import Optional, Tuple
 import torch
 
 from . import _lib
-from ._lib import DISK, SPHERICAL, EPI_RAW, EPI_DISK, EPI_SPHERICAL, EPI_BSDF, PREC_FP32, PREC_TC16  # noqa: F401
+from ._lib import (DISK, SPHERICAL, EPI_RAW, EPI_DISK, EPI_SPHERICAL, EPI_BSDF,  # noqa: F401
+                   PREC_FP32, PREC_TC16, PREC_TC16_EXP)
 
-_PREC_NAMES = {"fp32": PREC_FP32, "tc16": PREC_TC16}
+_PREC_NAMES = {"fp32": PREC_FP32, "tc16": PREC_TC16, "tc16_exp": PREC_TC16_EXP}
 _default_precision = _PREC_NAMES[os.environ.get("BSDFDIFF_PRECISION", "tc16")]
 
 # Philox counter words consumed per query by one sample call (1 Box-Muller draw + <= 64 von Mises rounds),

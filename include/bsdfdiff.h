@@ -54,6 +54,7 @@ extern "C" {
 /* arithmetic paths */
 #define BSDFDIFF_PREC_FP32  0   /* CUDA-core fp32 (parity path: matches the reference to ~1e-5)                 */
 #define BSDFDIFF_PREC_TC16  1   /* tcgen05: fp16 operands, fp32 TMEM accumulators (throughput path)             */
+#define BSDFDIFF_PREC_TC16_EXP 2 /* as TC16 but SiLU via fp32 exp instead of tanh.approx (accuracy cross-check)  */
 
 /* error codes */
 #define BSDFDIFF_OK            0
@@ -67,6 +68,7 @@ extern "C" {
 int         bsdfdiff_abi_version(void);
 const char* bsdfdiff_error_string(int code);
 int         bsdfdiff_last_cuda_error(void);          /* cudaError_t of the last failure on this thread */
+int         bsdfdiff_debug_timeout_flag(void);       /* 1 if a tensor-core kernel ever hit its mbarrier watchdog (syncs) */
 
 /* ---- weight packing (host side; the blob is then copied to the device by the caller) ------------------------
  * Flow net = bias-free MLP, layers given as row-major [rows,cols] fp32 matrices exactly as the checkpoints

@@ -56,10 +56,12 @@ def test_pack_flow_layout(built_lib, path):
 
     w1 = flow.layers[0]
     img = f16[: H * 32]
-    n_state = 3 if in_dim == 25 else 4
+    # layer-1 K order: 8 state slots (hi parts then lo parts), PE5(wi) at k = 8..29, two zero columns
+    state = [0, 1, 2, 2, 0, 1, None, None] if in_dim == 25 else [0, 1, 2, 3, 0, 1, 2, 3]
+    first_pe = 3 if in_dim == 25 else 4
     for n in (0, 7, 13, H - 1):
         for k in range(32):
-            src = k if k < in_dim else (k - in_dim if k - in_dim < n_state else None)
+            src = state[k] if k < 8 else (first_pe + k - 8 if k < 30 else None)
             want = np.float16(0.5 * w1[n, src]) if src is not None else np.float16(0)
             assert at(img, n, k, H) == want
     img = f16[H * 32: H * 32 + H * H]
