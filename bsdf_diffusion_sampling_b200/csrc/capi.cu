@@ -130,23 +130,25 @@ static int pack_from_layers(const std::vector<const float*>& Ws, const std::vect
     __half* h = reinterpret_cast<__half*>(out + hdr.off_f16);
     int src[32];
     tc_layer1_source_columns(domain, in_dim, src);
+    // every operand is stored as a HI image followed by a LO image: w = hi + lo with
+    // hi = fp16(w), lo = fp16(w - hi)
+    auto put = [&](__half* img, size_t lo_off, int n, int k, int N, float w) {
+        const __half hi = __float2half_rn(w);
+        img[umma_kmajor_index(n, k, N)] = hi;
+        img[lo_off + umma_kmajor_index(n, k, N)] = __float2half_rn(w - __half2float(hi));
+    };
     for (int n = 0; n < H; ++n)
-        for (int k = 0; k < 32; ++k) {
-            const float w = (src[k] >= 0) ? 0.5f * Ws[0][(size_t)n * in_dim + src[k]] : 0.0f;
-            h[umma_kmajor_index(n, k, H)] = __float2half_rn(w);
-        }
-    h += (size_t)H * 32;
+        for (int k = 0; k < 32; ++k)
+            put(h, (size_t)H * 32, n, k, H, (src[k] >= 0) ? 0.5f * Ws[0][(size_t)n * in_dim + src[k]] : 0.0f);
+    h += 2 * (size_t)H * 32;
     for (int l = 1; l < n_hidden; ++l) {
         for (int n = 0; n < H; ++n)
-            for (int k = 0; k < H; ++k)
-                h[umma_kmajor_index(n, k, H)] = __float2half_rn(0.5f * Ws[l][(size_t)n * H + k]);
-        h += (size_t)H * H;
+            for (int k = 0; k < H; ++k) put(h, (size_t)H * H, n, k, H, 0.5f * Ws[l][(size_t)n * H + k]);
+        h += 2 * (size_t)H * H;
     }
     for (int n = 0; n < 16; ++n)
-        for (int k = 0; k < H; ++k) {
-            const float w = (n < 2) ? Ws[n_layers - 1][(size_t)n * H + k] : 0.0f;
-            h[umma_kmajor_index(n, k, 16)] = __float2half_rn(w);
-        }
+        for (int k = 0; k < H; ++k)
+            put(h, (size_t)16 * H, n, k, 16, (n < 2) ? Ws[n_layers - 1][(size_t)n * H + k] : 0.0f);
 
     // aux: 0.5 * W1[:,0], 0.5 * W1[:,1], 0.5 * W1[:,2]  (first-layer tangent seeds, fp16-rounded like
     // the operand image so value and tangent paths see the same weights)

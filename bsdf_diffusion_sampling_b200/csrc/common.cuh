@@ -51,9 +51,11 @@ static_assert(sizeof(PackedHeader) == 64, "header must be 64 bytes");
 __host__ __device__ inline int f32_image_floats(int in_dim, int H, int n_hidden) {
     return in_dim * H + (n_hidden - 1) * H * H + 2 * H;
 }
-// fp16 image: first layer [H x 32], hidden [H x H] x (n_hidden-1), output [16 x H]
+// fp16 image: per layer a HI operand followed by a LO operand (W = hi + lo, each fp16; the value path
+// multiplies by both so weights carry ~22 mantissa bits, the tangent path uses hi only):
+// first layer 2 x [H x 32], hidden 2 x [H x H] x (n_hidden-1), output 2 x [16 x H]
 __host__ __device__ inline int f16_image_halves(int H, int n_hidden) {
-    return H * 32 + (n_hidden - 1) * H * H + 16 * H;
+    return 2 * (H * 32 + (n_hidden - 1) * H * H + 16 * H);
 }
 
 struct FlowParams {

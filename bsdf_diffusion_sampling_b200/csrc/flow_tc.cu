@@ -161,7 +161,7 @@ struct TcSmem {
     uint32_t pad[3];
     float base[kBaseFloats + 4];
     float aux[3 * 32];                      // 0.5*W1[:,0], 0.5*W1[:,1], 0.5*W1[:,2]
-    __align__(128) unsigned char w16[(32 * 32 + 5 * 32 * 32 + 16 * 32) * 2];   // up to 6 hidden layers of width 32
+    __align__(128) unsigned char w16[2 * (32 * 32 + 5 * 32 * 32 + 16 * 32) * 2];   // hi+lo images, <= 6 hidden layers
 };
 
 template <bool TANGENTS, int ACT>
@@ -222,26 +222,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                     pa[g] ^= 1u;
                     tc_fence_after();
                     const uint32_t tg = tmem_base + g * kColsPerGroup;
+                    // Each layer's operand image = HI [N x 32] then LO [N x 32] (W = hi + lo).  The value
+                    // path accumulates A.hi + A.lo (weights effectively ~22 bits), tangents use hi only.
                     if (type == 0) {
-                        // layer 1: D_z = A1 . W1^T   (K = 32 -> two K=16 instructions)
-                        const uint64_t b0 = make_b_desc(w_base, 512, 128);
-                        mma_ts(tg + kColD, tg + kColA1, b0, idesc32, 0u);
+                        // layer 1: D_z = A1 . W1^T   (K = 32 -> two K=16 instructions per operand image)
+                        mma_ts(tg + kColD, tg + kColA1, make_b_desc(w_base, 512, 128), idesc32, 0u);
                         mma_ts(tg + kColD, tg + kColA1 + 8, make_b_desc(w_base + 1024, 512, 128), idesc32, 1u);
+                        mma_ts(tg + kColD, tg + kColA1, make_b_desc(w_base + 2048, 512, 128), idesc32, 1u);
+                        mma_ts(tg + kColD, tg + kColA1 + 8, make_b_desc(w_base + 3072, 512, 128), idesc32, 1u);
                     } else if (type < NH) {
-                        const uint32_t wl = w_base + 2048u * type;              // hidden layer (type+1)
+                        const uint32_t wl = w_base + 4096u * type;              // hidden layer (type+1)
                         const uint64_t b0 = make_b_desc(wl, 512, 128), b1 = make_b_desc(wl + 1024, 512, 128);
+                        mma_ts(tg + kColD, tg + kColA, b0, idesc32, 0u);
+                        mma_ts(tg + kColD, tg + kColA + 8, b1, idesc32, 1u);
+                        mma_ts(tg + kColD, tg + kColA, make_b_desc(wl + 2048, 512, 128), idesc32, 1u);
+                        mma_ts(tg + kColD, tg + kColA + 8, make_b_desc(wl + 3072, 512, 128), idesc32, 1u);
+                        if (TANGENTS) {
 #pragma unroll
-                        for (int c = 0; c < (TANGENTS ? 3 : 1); ++c) {
-                            mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c, b0, idesc32, 0u);
-                            mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b1, idesc32, 1u);
+                            for (int c = 1; c < 3; ++c) {
+                                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c, b0, idesc32, 0u);
+                                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b1, idesc32, 1u);
+                            }
                         }
                     } else {
-                        const uint32_t wl = w_base + 2048u * NH;                // output layer, N = 16
+                        const uint32_t wl = w_base + 4096u * NH;                // output layer, N = 16
                         const uint64_t b0 = make_b_desc(wl, 256, 128), b1 = make_b_desc(wl + 512, 256, 128);
+                        mma_ts(tg + kColD, tg + kColA, b0, idesc16, 0u);
+                        mma_ts(tg + kColD, tg + kColA + 8, b1, idesc16, 1u);
+                        mma_ts(tg + kColD, tg + kColA, make_b_desc(wl + 1024, 256, 128), idesc16, 1u);
+                        mma_ts(tg + kColD, tg + kColA + 8, make_b_desc(wl + 1536, 256, 128), idesc16, 1u);
+                        if (TANGENTS) {
 #pragma unroll
-                        for (int c = 0; c < (TANGENTS ? 3 : 1); ++c) {
-                            mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c, b0, idesc16, 0u);
-                            mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b1, idesc16, 1u);
+                            for (int c = 1; c < 3; ++c) {
+                                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c, b0, idesc16, 0u);
+                                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b1, idesc16, 1u);
+                            }
                         }
                     }
                     tc_commit(smem_u32(&S.d_ready[g]));

@@ -158,10 +158,10 @@ static void flow_step(const float* flow, int in_dim, int H, int n_hidden, int do
 }
 
 static void euler(const float* flow, int in_dim, int H, int n_hidden, int domain, int T, int reverse,
-                  float x[2], const float wi[2], float* R_out) {
+                  float x[2], const float wi[2], float* R_out, float* mindet_out) {
     float e[PE5];
     pe(wi, 5, e);
-    float R = 1.0f;
+    float R = 1.0f, mind = FLT_MAX;
     const float inv_t = (float)(1.0 / T), sgn = reverse ? -1.0f : 1.0f;
     for (int t = 0; t < T; ++t) {
         float alpha = (float)(reverse ? (1.0 - (double)t / T) : ((double)t / T));
@@ -171,10 +171,12 @@ static void euler(const float* flow, int in_dim, int H, int n_hidden, int domain
         float j10 = sgn * inv_t * du[1], j11 = 1.0f + sgn * inv_t * dv[1];
         float det = j00 * j11 - j01 * j10;
         R = reverse ? R * det : R / det;
+        mind = fminf(mind, fabsf(det));
         x[0] += sgn * inv_t * d[0];
         x[1] += sgn * inv_t * d[1];
     }
     *R_out = R;
+    if (mindet_out) *mindet_out = mind;
 }
 
 static void cart_to_spher(const float w[3], float out[2]) {
@@ -194,7 +196,8 @@ static float inv_sin_clamped(float x, float y, int use_abs) {
  * wi is [n,2] domain coords for epilogue 0, [n,3] local-frame directions otherwise.
  * x0 (replayed base sample, [n,2]) is REQUIRED: the oracle never draws random numbers itself. */
 int bsdf_oracle_sample(int domain, int epilogue, int T, int64_t n, const float* wi, const float* flow, int in_dim,
-                       int H, int n_hidden, const float* base, const float* x0, float* out_dir, float* out_pdf) {
+                       int H, int n_hidden, const float* base, const float* x0, float* out_dir, float* out_pdf,
+                       float* out_mindet /* optional: min_t |det J_t| per query (conditioning of the pdf) */) {
     if (!x0 || H > MAXH || in_dim > 32) return -1;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
@@ -205,7 +208,7 @@ int bsdf_oracle_sample(int domain, int epilogue, int T, int64_t n, const float* 
         float x[2] = {x0[2 * i], x0[2 * i + 1]};
         float p0 = expf(domain == 0 ? logp_disk(base, x, w) : logp_sph(base, x, w));
         float R;
-        euler(flow, in_dim, H, n_hidden, domain, T, 0, x, w, &R);
+        euler(flow, in_dim, H, n_hidden, domain, T, 0, x, w, &R, out_mindet ? out_mindet + i : 0);
         float pdf = p0 * R;
         if (epilogue == 0) {
             out_dir[2 * i] = x[0]; out_dir[2 * i + 1] = x[1]; out_pdf[i] = pdf;
@@ -228,7 +231,7 @@ int bsdf_oracle_sample(int domain, int epilogue, int T, int64_t n, const float* 
 }
 
 int bsdf_oracle_pdf(int domain, int epilogue, int T, int64_t n, const float* wo, const float* wi, const float* flow,
-                    int in_dim, int H, int n_hidden, const float* base, float* out_pdf) {
+                    int in_dim, int H, int n_hidden, const float* base, float* out_pdf, float* out_mindet /* optional */) {
     if (H > MAXH || in_dim > 32) return -1;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
@@ -238,7 +241,7 @@ int bsdf_oracle_pdf(int domain, int epilogue, int T, int64_t n, const float* wo,
         else { cart_to_spher(wi + 3 * i, w); cart_to_spher(wo + 3 * i, x); }
         float theta_o = x[0];
         float R;
-        euler(flow, in_dim, H, n_hidden, domain, T, 1, x, w, &R);
+        euler(flow, in_dim, H, n_hidden, domain, T, 1, x, w, &R, out_mindet ? out_mindet + i : 0);
         float pdf = expf(domain == 0 ? logp_disk(base, x, w) : logp_sph(base, x, w)) * R;
         if (epilogue == 1) {
             int ok = (wi[3 * i + 2] > 0.f) && (wo[3 * i + 2] > 0.f);

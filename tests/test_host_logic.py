@@ -54,20 +54,25 @@ def test_pack_flow_layout(built_lib, path):
     def at(img, n, k, N):
         return img[((k // 8) * (N // 8) + n // 8) * 64 + (n % 8) * 8 + k % 8]
 
+    def hi_lo(w):
+        hi = np.float16(w)
+        return hi, np.float16(np.float32(w) - np.float32(hi))
+
     w1 = flow.layers[0]
-    img = f16[: H * 32]
+    img_hi, img_lo = f16[: H * 32], f16[H * 32: 2 * H * 32]
     # layer-1 K order: 8 state slots (hi parts then lo parts), PE5(wi) at k = 8..29, two zero columns
     state = [0, 1, 2, 2, 0, 1, None, None] if in_dim == 25 else [0, 1, 2, 3, 0, 1, 2, 3]
     first_pe = 3 if in_dim == 25 else 4
     for n in (0, 7, 13, H - 1):
         for k in range(32):
             src = state[k] if k < 8 else (first_pe + k - 8 if k < 30 else None)
-            want = np.float16(0.5 * w1[n, src]) if src is not None else np.float16(0)
-            assert at(img, n, k, H) == want
-    img = f16[H * 32: H * 32 + H * H]
-    assert at(img, 5, 9, H) == np.float16(0.5 * flow.layers[1][5, 9])
-    img = f16[H * 32 + (nh - 1) * H * H:]
-    assert at(img, 1, 17, 16) == np.float16(flow.layers[-1][1, 17]) and at(img, 2, 3, 16) == 0
+            want = hi_lo(np.float32(0.5) * w1[n, src]) if src is not None else (np.float16(0), np.float16(0))
+            assert (at(img_hi, n, k, H), at(img_lo, n, k, H)) == want
+    l2 = f16[2 * H * 32: 2 * H * 32 + 2 * H * H]
+    assert (at(l2[: H * H], 5, 9, H), at(l2[H * H:], 5, 9, H)) == hi_lo(np.float32(0.5) * flow.layers[1][5, 9])
+    out = f16[2 * H * 32 + 2 * (nh - 1) * H * H:]
+    assert (at(out[: 16 * H], 1, 17, 16), at(out[16 * H:], 1, 17, 16)) == hi_lo(flow.layers[-1][1, 17])
+    assert at(out, 2, 3, 16) == 0 and out.size == 2 * 16 * H
     aux = np.frombuffer(blob, np.float32, h["n_aux"] // 4, h["off_aux"])
     assert np.array_equal(aux[:H], (0.5 * w1[:, 0]).astype(np.float16).astype(np.float32))
 
