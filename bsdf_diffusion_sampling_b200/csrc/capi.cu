@@ -32,6 +32,10 @@ extern "C" int bsdfdiff_last_cuda_error(void) { return g_last_cuda_error; }
 
 extern "C" int bsdfdiff_debug_timeout_flag(void) { return (int)tc_timeout_flag(); }
 
+extern "C" int bsdfdiff_debug_profile_fetch(unsigned long long* out, int max_elems) {
+    return tc_profile_fetch(out, max_elems);
+}
+
 extern "C" int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail_cuda();
@@ -200,7 +204,12 @@ extern "C" int bsdfdiff_pack_flow_tcnn(const float* p, int in_dim, int out_dim, 
 static int dispatch(int precision, const FlowParams& P, cudaStream_t stream) {
     int rc;
     if (precision == BSDFDIFF_PREC_FP32 || P.T == 0) rc = launch_simt(P, stream);
-    else if (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP) rc = launch_tc(P, stream, precision);
+    else if (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP) {
+        rc = launch_tc(P, stream, precision);
+        // shapes the tcgen05 kernel does not cover yet (64-wide reflow teacher nets) run on the CUDA-core
+        // kernel of the same library -- still a GPU path, never a CPU fallback
+        if (rc == -2) rc = launch_simt(P, stream);
+    }
     else return BSDFDIFF_EINVAL;
     if (rc == -3) return fail_cuda();
     return rc;

@@ -34,7 +34,8 @@ def _as_cuda(t: torch.Tensor) -> torch.Tensor:
 def network_sampling_disk(D_base, D_sample, omega_i, T=4, *, x0=None, seed=None, offset=0, precision=None):
     omega_i = _as_cuda(omega_i)
     flow, base = _packed(D_base, D_sample, omega_i.device)
-    x, pdf, _ = ops.sample(omega_i, flow, base, T, x0=x0, seed=seed, offset=offset, precision=precision)
+    x, pdf, _ = ops.sample(omega_i, flow, base, T, x0=x0, seed=seed, offset=offset, precision=precision,
+                           return_x0=False)
     return x, pdf
 
 
@@ -47,7 +48,8 @@ def network_pdf_disk(D_base, D_sample, omega_o, omega_i, T=4, *, precision=None)
 def network_sampling_spherical(D_base, D_sample, omega_i, T=8, *, x0=None, seed=None, offset=0, precision=None):
     omega_i = _as_cuda(omega_i)
     flow, base = _packed(D_base, D_sample, omega_i.device)
-    x, pdf, _ = ops.sample(omega_i, flow, base, T, x0=x0, seed=seed, offset=offset, precision=precision)
+    x, pdf, _ = ops.sample(omega_i, flow, base, T, x0=x0, seed=seed, offset=offset, precision=precision,
+                           return_x0=False)
     return x, pdf
 
 

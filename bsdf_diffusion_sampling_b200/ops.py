@@ -73,25 +73,27 @@ def next_philox(device) -> Tuple[int, int]:
 @torch.library.custom_op("bsdfdiff::sample", mutates_args=(), device_types="cuda")
 def _sample_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor, x0: Optional[torch.Tensor],
                precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
-               seed: int, offset: int, first_index: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               seed: int, offset: int, first_index: int,
+               want_x0: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     n = wi.shape[0]
     out_dir = torch.empty((n, 2 if epilogue == EPI_RAW else 3), dtype=torch.float32, device=wi.device)
     out_pdf = torch.empty((n,), dtype=torch.float32, device=wi.device)
-    out_x0 = torch.empty((n, 2), dtype=torch.float32, device=wi.device)
+    out_x0 = torch.empty((n if want_x0 else 0, 2), dtype=torch.float32, device=wi.device)
     with torch.cuda.device(wi.device):
         rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
                                       flow_blob.data_ptr() if flow_blob is not None else None,
                                       hidden, n_hidden, base.data_ptr(), x0.data_ptr() if x0 is not None else None,
                                       seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(),
-                                      out_x0.data_ptr(), _stream(wi))
+                                      out_x0.data_ptr() if want_x0 else None, _stream(wi))
     _lib.check(rc, "bsdfdiff_sample")
     return out_dir, out_pdf, out_x0
 
 
 @_sample_op.register_fake
-def _(wi, flow_blob, base, x0, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index):
+def _(wi, flow_blob, base, x0, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, want_x0):
     n = wi.shape[0]
-    return (wi.new_empty((n, 2 if epilogue == EPI_RAW else 3)), wi.new_empty((n,)), wi.new_empty((n, 2)))
+    return (wi.new_empty((n, 2 if epilogue == EPI_RAW else 3)), wi.new_empty((n,)),
+            wi.new_empty((n if want_x0 else 0, 2)))
 
 
 @torch.library.custom_op("bsdfdiff::pdf", mutates_args=(), device_types="cuda")
@@ -165,8 +167,9 @@ class NullFlow:
 
 def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,
            x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0, first_index: int = 0,
-           precision=None):
-    """-> (dir [n,2|3], pdf [n], x0 [n,2]).  ``flow`` is a ``weights.PackedFlow``."""
+           precision=None, return_x0: bool = True):
+    """-> (dir [n,2|3], pdf [n], x0 [n,2]).  ``flow`` is a ``weights.PackedFlow``.
+    ``return_x0=False`` skips materialising the base sample (8 B/query of HBM writes); x0 is then empty."""
     _require_cuda(wi, "sample")
     wi = _f32c(wi)
     if T < 0 or (T == 0) != (flow.blob is None):
@@ -177,7 +180,7 @@ def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int 
     elif seed is None:
         seed, offset = next_philox(wi.device)
     return _sample_op(wi, flow.blob, base, x0, _resolve_precision(precision), flow.domain, epilogue, int(T),
-                      flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index))
+                      flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), bool(return_x0))
 
 
 def pdf(wo: torch.Tensor, wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,

@@ -84,7 +84,8 @@ class NeuralBSDFSampler:
     def sample(self, wi: torch.Tensor, *, x0=None, seed=None, offset=0, first_index=0):
         """wi [N,3] local frame -> (wo [N,3], pdf_omega [N]) == (bs.wo, bs.pdf as first assigned)."""
         wo, pdf, _ = ops.sample(wi, self.flow, self.base, self.T, epilogue=self.epilogue, x0=x0, seed=seed,
-                                offset=offset, first_index=first_index, precision=self.precision)
+                                offset=offset, first_index=first_index, precision=self.precision,
+                                return_x0=False)
         return wo, pdf
 
     def pdf(self, wi: torch.Tensor, wo: torch.Tensor) -> torch.Tensor:

@@ -161,7 +161,7 @@ static void euler(const float* flow, int in_dim, int H, int n_hidden, int domain
                   float x[2], const float wi[2], float* R_out, float* mindet_out) {
     float e[PE5];
     pe(wi, 5, e);
-    float R = 1.0f, mind = FLT_MAX;
+    float R = 1.0f, mind = FLT_MAX, amp = 1.0f;
     const float inv_t = (float)(1.0 / T), sgn = reverse ? -1.0f : 1.0f;
     for (int t = 0; t < T; ++t) {
         float alpha = (float)(reverse ? (1.0 - (double)t / T) : ((double)t / T));
@@ -172,11 +172,19 @@ static void euler(const float* flow, int in_dim, int H, int n_hidden, int domain
         float det = j00 * j11 - j01 * j10;
         R = reverse ? R * det : R / det;
         mind = fminf(mind, fabsf(det));
+        /* largest singular value of the step map's Jacobian: how much a state error grows in this step */
+        float fro = j00 * j00 + j01 * j01 + j10 * j10 + j11 * j11;
+        float smax = sqrtf(0.5f * (fro + sqrtf(fmaxf(fro * fro - 4.f * det * det, 0.f))));
+        amp *= fmaxf(1.0f, smax);
         x[0] += sgn * inv_t * d[0];
         x[1] += sgn * inv_t * d[1];
     }
     *R_out = R;
-    if (mindet_out) *mindet_out = mind;
+    /* Conditioning weight in (0,1] of the pdf w.r.t. rounding inside the flow (used by the tests to state the
+     * reduced-precision bar per unit of condition number):  pdf = p0 (/|*) prod det_t, so an absolute error in a
+     * step determinant is a relative pdf error ~ 1/|det_t|  -> factor min(1, min|det|/0.2);  a state error made
+     * early is amplified by the later steps' Jacobians -> factor min(1, 16 / prod max(1, sigma_max(J_t))). */
+    if (mindet_out) *mindet_out = fminf(1.0f, mind / 0.2f) * fminf(1.0f, 16.0f / amp);
 }
 
 static void cart_to_spher(const float w[3], float out[2]) {
@@ -197,7 +205,7 @@ static float inv_sin_clamped(float x, float y, int use_abs) {
  * x0 (replayed base sample, [n,2]) is REQUIRED: the oracle never draws random numbers itself. */
 int bsdf_oracle_sample(int domain, int epilogue, int T, int64_t n, const float* wi, const float* flow, int in_dim,
                        int H, int n_hidden, const float* base, const float* x0, float* out_dir, float* out_pdf,
-                       float* out_mindet /* optional: min_t |det J_t| per query (conditioning of the pdf) */) {
+                       float* out_mindet /* optional: conditioning weight in (0,1] per query, see euler() */) {
     if (!x0 || H > MAXH || in_dim > 32) return -1;
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < n; ++i) {
@@ -243,6 +251,23 @@ int bsdf_oracle_pdf(int domain, int epilogue, int T, int64_t n, const float* wo,
         float R;
         euler(flow, in_dim, H, n_hidden, domain, T, 1, x, w, &R, out_mindet ? out_mindet + i : 0);
         float pdf = expf(domain == 0 ? logp_disk(base, x, w) : logp_sph(base, x, w)) * R;
+        if (out_mindet) {
+            /* conditioning of pdf() has a second factor: the base density is evaluated at the END of the
+             * reverse flow, so an endpoint error dx shows up as a relative pdf error |grad log p_base| * dx.
+             * Fold it into the conditioning weight where that gradient exceeds 25 (narrow base). */
+            float p[4], g0, g1;
+            base_eval(base, w, p);
+            if (domain == 0) {
+                g0 = (x[0] - p[0]) / (expf(p[2]) * expf(p[2]));
+                g1 = (x[1] - p[1]) / (expf(p[3]) * expf(p[3]));
+            } else {
+                float sc = expf(p[1]) + 1e-3f;
+                g0 = (x[0] - p[0]) / (sc * sc);
+                g1 = (softplusf_(p[3]) + 1e-3f) * sinf(x[1] - p[2]);
+            }
+            float gn = sqrtf(g0 * g0 + g1 * g1);
+            if (gn > 25.f) out_mindet[i] *= 25.f / gn;
+        }
         if (epilogue == 1) {
             int ok = (wi[3 * i + 2] > 0.f) && (wo[3 * i + 2] > 0.f);
             pdf = ok ? pdf * wo[3 * i + 2] : 0.f;

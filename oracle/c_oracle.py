@@ -52,7 +52,7 @@ def num_threads() -> int:
 
 
 def sample(flow, base, wi, T, x0, epilogue=EPI_RAW, with_mindet=False):
-    """-> (dir [n,2] raw or [n,3] plugin, pdf [n]) [, min_t |det J_t| [n] if with_mindet]."""
+    """-> (dir [n,2] raw or [n,3] plugin, pdf [n]) [, conditioning weight in (0,1] [n] if with_mindet: 1 = well-conditioned pdf, see bsdf_oracle.c euler()]."""
     wi, x0 = _f(wi), _f(x0)
     n = wi.shape[0]
     flat, in_dim, H, nh = _flow_args(flow)
