@@ -79,6 +79,11 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {                   // exactly one lane of a converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void group_sync(int g) {            // named barrier 1+g over the group's 128 threads
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(128) : "memory");
 }
@@ -271,7 +276,9 @@ __device__ unsigned long long g_tc_prof[148 * 12 * kProfSlots];
 template <bool TANGENTS, int ACT, bool PROF>
 __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams P) {
     __shared__ TcSmem S;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle so the compiler can prove it warp-uniform: TMEM addresses and MMA
+    // descriptors then live in uniform registers (no per-MMA R2UR/ELECT waterfall)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     unsigned long long prof[kProfSlots] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = PROF ? clock64() : 0;
     const long long tstart = tlast;
@@ -301,14 +308,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = S.tmem_base;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
 
     const long long n_tiles = (P.n + kTile - 1) / kTile;
     // tile list of this CTA: blockIdx.x, +gridDim.x, ...; group g takes every kGroups-th entry
     const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     const int g = warp >> 2, q = warp & 3;
-    const bool issuer = (q == 0) && (lane == 0);
     const uint32_t tg_mma = tmem_base + g * kColsPerGroup;                   // lane field 0: MMA operand addresses
     const uint32_t tg = tg_mma + ((uint32_t)(q * 32) << 16);                 // this warp's 32-lane window
     const uint32_t bar_d = smem_u32(&S.d_ready[g]);
@@ -318,7 +324,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     const float inv_t = (float)(1.0 / (double)P.T);
     const float sgn = (P.mode == kModePdf) ? -1.0f : 1.0f;
     const float step = sgn * inv_t;
-    if (issuer) ok = mbar_wait(smem_u32(&S.w_bar), 0);                       // weights have landed in smem
+    if (q == 0) ok = mbar_wait(smem_u32(&S.w_bar), 0);                      // weights have landed in smem
 
     for (long long k = g; k < my_tiles && ok; k += kGroups) {
         const long long tile = blockIdx.x + k * gridDim.x;
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             tc_fence_before();
             group_sync(g);
             PROF_T(3);
-            if (issuer) { tc_fence_after(); issue_round<TANGENTS>(0, NH, tg_mma, w_base, bar_d); }
+            if (q == 0 && elect_one()) { tc_fence_after(); issue_round<TANGENTS>(0, NH, tg_mma, w_base, bar_d); }
             __syncwarp();
             PROF_T(4);
 
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             tc_fence_before();
             group_sync(g);
             PROF_T(3);
-            if (issuer) { tc_fence_after(); issue_round<TANGENTS>(1, NH, tg_mma, w_base, bar_d); }
+            if (q == 0 && elect_one()) { tc_fence_after(); issue_round<TANGENTS>(1, NH, tg_mma, w_base, bar_d); }
             __syncwarp();
             PROF_T(4);
 
@@ -468,7 +474,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 tc_fence_before();
                 group_sync(g);
                 PROF_T(3);
-                if (issuer) { tc_fence_after(); issue_round<TANGENTS>(l + 1, NH, tg_mma, w_base, bar_d); }
+                if (q == 0 && elect_one()) { tc_fence_after(); issue_round<TANGENTS>(l + 1, NH, tg_mma, w_base, bar_d); }
                 __syncwarp();
                 PROF_T(4);
             }
