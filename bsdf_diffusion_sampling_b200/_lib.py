@@ -21,7 +21,6 @@ ABI_VERSION = 1
 
 EXPORTS = [
     "bsdfdiff_abi_version", "bsdfdiff_error_string", "bsdfdiff_last_cuda_error", "bsdfdiff_debug_timeout_flag",
-    "bsdfdiff_debug_profile_fetch",
     "bsdfdiff_device_info",
     "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn",
     "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",

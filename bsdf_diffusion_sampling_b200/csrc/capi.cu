@@ -32,10 +32,6 @@ extern "C" int bsdfdiff_last_cuda_error(void) { return g_last_cuda_error; }
 
 extern "C" int bsdfdiff_debug_timeout_flag(void) { return (int)tc_timeout_flag(); }
 
-extern "C" int bsdfdiff_debug_profile_fetch(unsigned long long* out, int max_elems) {
-    return tc_profile_fetch(out, max_elems);
-}
-
 extern "C" int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail_cuda();

@@ -303,7 +303,6 @@ __device__ __forceinline__ void store_pdf(const FlowParams& P, long long i, floa
 int launch_simt(const FlowParams& P, cudaStream_t stream);
 int launch_tc(const FlowParams& P, cudaStream_t stream, int variant);
 unsigned int tc_timeout_flag();
-int tc_profile_fetch(unsigned long long* out, int max_elems);
 int launch_mlp_forward_simt(long long n, const float* in, int in_dim, const unsigned char* flow, int H, int n_hidden,
                             float* out, cudaStream_t stream);
 

@@ -2,21 +2,30 @@
 //
 // One persistent CTA per SM, kGroups worker groups of 128 threads (4 warps; thread <-> TMEM lane <->
 // query row).  Each group owns one 128-query tile at a time and runs the WHOLE T-step flow for it on
-// chip; the groups are independent pipelines that overlap each other's tensor-core round trips:
+// chip; the groups are independent pipelines that overlap each other's tensor-core round trips
+// (TMEM holds exactly three tiles: 3 x 160 of the 512 columns).
 //
 //   per tile:  PE5(wi) -> fp16 -> TMEM A1[:,8:30];  base net, x0 (Philox or replay), p0   (fp32)
-//   per step:  state (hi/lo fp16 split) -> TMEM A1[:,0:8]
-//              bar.sync(group) ; elected thread:  D_z  = A1 . W1^T                 (K=32, N=32)
-//              tcgen05.ld D_z ; SiLU / SiLU' ; tangent seeds -> fp16 -> TMEM A_h, A_u, A_v
-//              bar.sync(group) ; elected thread:  D_z,D_u,D_v = A_{h,u,v} . Wl^T   (x (n_hidden-1))
-//              ...
-//              bar.sync(group) ; elected thread:  D = A . Wout^T                   (N=16)
-//              tcgen05.ld d, dd/dx0, dd/dx1 (6 floats) ; det J, R, Euler update in fp32 registers
+//   per step:  state (hi/lo fp16 split) -> A1[:,0:8];  tangent seeds d(state)/dx -> A_u, A_v (K chunk 0)
+//              round 0      :  D_z = A1 . W1^T (K=32),  D_u = A_u . W1^T, D_v = A_v . W1^T (K=16)
+//              rounds 1..H-1:  D_z, D_u, D_v = A_{h,u,v} . Wl^T                              (K=32, N=32)
+//              after every round the SAME code runs:  tcgen05.ld z, du, dv ; t = tanh(z/2) ;
+//                   h = silu(z), s = silu'(z) ; A_h = h, A_u = s du, A_v = s dv  (fp16, tcgen05.st)
+//              output round :  D = A . Wout^T (N=16) ; d, dd/dx0, dd/dx1 (6 floats) ;
+//                   det J, R, Euler update in fp32 registers
 //   epilogue:  base log-prob (pdf mode), domain mapping + Jacobian, store wo / pdf
 //
-// The thread that issues a group's tcgen05.mma is one elected lane of the group itself (after a
-// 128-thread named barrier), so there is no separate control warp competing for issue slots and no
-// second mbarrier hop; completion comes back through tcgen05.commit -> mbarrier d_ready[g].
+// The first layer's tangents are produced by the tensor core as well: the seed operand is the derivative
+// of the first-layer input row w.r.t. the state (a unit vector for x, theta; (cos phi, -sin phi) on the
+// sin/cos columns for phi), so D_u = W1 . d(in)/dx0 and every round, first or hidden, is the same
+// instruction stream -- there is no per-neuron table lookup and the activation loop exists once.
+//
+// Synchronisation per round (measured chain ~320 cycles beyond the loads/stores, profiles/microbench):
+//   tcgen05.wait::st ; tcgen05.fence::before_thread_sync ; bar.sync (group, 128 threads) ;
+//   one elected lane of the group's first warp: fence::after, 6-8 x tcgen05.mma, tcgen05.commit -> mbarrier ;
+//   all 128 threads: mbarrier.try_wait (hardware-suspended) ; fence::after ; tcgen05.ld
+// All MMA operands are warp-uniform (TMEM base through a shuffle, compile-time offsets), so the MMAs issue
+// back to back from uniform registers.
 //
 // Operands: A (activations; value + two tangent columns = three M=128 row blocks sharing B) lives in
 // TMEM as fp16 (tcgen05.mma ".ts" form), written by the worker threads with tcgen05.st -- activations
@@ -29,14 +38,14 @@
 // tanh-form sigmoid: hidden-layer weights are pre-scaled by 1/2 (exact), so the MMA yields zh = z/2 and
 // duh = du/2:   t = tanh(zh);  silu(z) = zh + zh t;  2 silu'(z) = (1 + t) + silu(z) (1 - t);
 // u_out = 2 silu'(z) * duh  -> one MUFU op per activation and no rescaling.  The fp32 arithmetic is
-// issued as packed f32x2 instructions (two activations per issue slot).
+// issued as packed f32x2 instructions (two activations per issue slot).  MUFU.TANH (16 / clk / SM) is the
+// binding pipe of this kernel; the FMA pipe (f32x2 at half rate) and the ALU pipe (F2FP packs) overlap it.
 //
 // TMEM map (512 columns allocated; per group 160 columns at g*160):
 //   [  0, 96)  D_z | D_u | D_v   fp32 accumulators, 32 columns each (output round uses 16 of each)
 //   [ 96,144)  A_h | A_u | A_v   fp16 operands, K=32 -> 16 columns each
 //   [144,160)  A1                first-layer operand: cols 0..3 state (rewritten per step), 4..15 PE5(wi)
 #include "common.cuh"
-#include <cstdlib>
 
 namespace bsdfdiff {
 
@@ -60,20 +69,28 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ unsigned int g_tc_timeout_flag = 0;
 
-// Bounded wait: a protocol bug must never hang the GPU.  try_wait suspends the warp in hardware (up to
-// the hint) instead of spinning, so waiting warps do not steal issue slots from the computing ones.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done = 0;
-    for (int it = 0; it < (1 << 22); ++it) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(bar), "r"(parity), "r"(10000u) : "memory");
-        if (done) return true;
-    }
+__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
+    return done;
+}
+// Watchdog path (never taken by a correct protocol): keep polling for a bounded time, then record the fault and
+// abort the launch -- a protocol bug must never hang the GPU.
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (int it = 0; it < (1 << 20); ++it)
+        if (mbar_try(bar, parity)) return;
     atomicExch(&g_tc_timeout_flag, 1u);
-    return false;
+    __trap();
+}
+// try_wait suspends the warp in hardware (up to the hint) instead of spinning, so waiting warps do not steal
+// issue slots from the computing ones; the first probe almost always succeeds.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -94,13 +111,14 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem]^T, kind::f16 (fp16 operands, fp32 accumulate)
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+// D[tmem] (+)= A[tmem] . B[smem]^T, kind::f16 (fp16 operands, fp32 accumulate); ACC is a compile-time flag
+template <int ACC>
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -126,10 +144,13 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
-__device__ __forceinline__ float f16_round(float x) { return __half2float(__float2half_rn(x)); }
+// fp32 value of the low / high half of a packed fp16 pair
+__device__ __forceinline__ float h2_lo(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p & 0xffffu))); }
+__device__ __forceinline__ float h2_hi(uint32_t p) { return __half2float(__ushort_as_half((unsigned short)(p >> 16))); }
 
 // packed fp32 pairs (sm_100 f32x2 ALU instructions: two lanes per issue slot)
 typedef unsigned long long f32x2;
@@ -193,16 +214,33 @@ __device__ __forceinline__ void silu_pair2(float zh0, float zh1, f32x2& h, f32x2
     }
 }
 
-// PE5(v) with two accurate sincosf and four double-angle steps (abs error ~1e-6, far below fp16 ulp)
+// One activation pass over 16 neurons of this thread's row: z, du, dv (fp32, from TMEM) -> fp16 operand words.
+template <bool TANGENTS, int ACT>
+__device__ __forceinline__ void activate16(const float* z, const float* du, const float* dv,
+                                           uint32_t* ph, uint32_t* pu, uint32_t* pv) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        f32x2 h, s2;
+        silu_pair2<ACT>(z[j], z[j + 1], h, s2);
+        ph[j >> 1] = pack_h2(h);
+        if (TANGENTS) {
+            pu[j >> 1] = pack_h2(mul2(s2, pk2(du[j], du[j + 1])));
+            pv[j >> 1] = pack_h2(mul2(s2, pk2(dv[j], dv[j + 1])));
+        }
+    }
+}
+
+// PE5(v): two MUFU sin/cos pairs (arguments are bounded: |v| <= pi for every domain) and four double-angle
+// steps; abs error ~1e-5 at the highest frequency, well below the fp16 ulp of the operand it feeds.
 __device__ __forceinline__ void pe5_fast(float v0, float v1, float* e) {
     float s0, c0, s1, c1;
-    sincosf(v0, &s0, &c0);
-    sincosf(v1, &s1, &c1);
+    __sincosf(v0, &s0, &c0);
+    __sincosf(v1, &s1, &c1);
     e[0] = v0; e[1] = v1;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         e[2 + 4 * k + 0] = s0; e[2 + 4 * k + 1] = s1; e[2 + 4 * k + 2] = c0; e[2 + 4 * k + 3] = c1;
-        const float ns0 = 2.0f * s0 * c0, ns1 = 2.0f * s1 * c1;
+        const float ns0 = (s0 + s0) * c0, ns1 = (s1 + s1) * c1;
         c0 = fmaf(c0, c0, -s0 * s0); c1 = fmaf(c1, c1, -s1 * s1);
         s0 = ns0; s1 = ns1;
     }
@@ -213,75 +251,107 @@ struct TcSmem {
     unsigned long long w_bar;
     uint32_t tmem_base;
     uint32_t pad[3];
-    float base[kBaseFloats + 4];
-    float4 aux[32];                         // per neuron: 0.5*W1[j,0], 0.5*W1[j,1], 0.5*W1[j,2], 0
+    // base net re-laid for 128-bit broadcast loads: w1t[k][j] (k < 14, j < 16), b1[16], wot[j][c] (c < 4), bo[4]
+    __align__(16) float bw1t[kPE3 * 16];
+    __align__(16) float bb1[16];
+    __align__(16) float bwot[16 * 4];
+    __align__(16) float bbo[4];
     __align__(128) unsigned char w16[2 * (32 * 32 + 5 * 32 * 32 + 16 * 32) * 2];   // hi+lo images, <= 6 hidden layers
 };
 
-// Issue one round of MMAs for a group (executed by ONE thread).  Each layer's operand image = HI [N x 32]
-// then LO [N x 32] (W = hi + lo): the value path accumulates A.hi^T + A.lo^T, tangents use hi only.
+// base net p = Wo silu(W1 PE3(e) + b1) + bo from the shared-memory copy (rendering/utils/model.py:382-386)
+__device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, float p[4]) {
+    f32x2 z[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 b = reinterpret_cast<const float4*>(S.bb1)[q];
+        z[2 * q] = pk2(b.x, b.y); z[2 * q + 1] = pk2(b.z, b.w);
+    }
+#pragma unroll
+    for (int k = 0; k < kPE3; ++k) {
+        const f32x2 ek = pk2(e[k], e[k]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 w = reinterpret_cast<const float4*>(S.bw1t)[k * 4 + q];
+            z[2 * q] = fma2(ek, pk2(w.x, w.y), z[2 * q]);
+            z[2 * q + 1] = fma2(ek, pk2(w.z, w.w), z[2 * q + 1]);
+        }
+    }
+    const float4 bo = *reinterpret_cast<const float4*>(S.bbo);
+    f32x2 p01 = pk2(bo.x, bo.y), p23 = pk2(bo.z, bo.w);
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        float z0, z1;
+        upk2(z[j >> 1], z0, z1);
+        const float h0 = z0 * __fdividef(1.0f, 1.0f + __expf(-z0));
+        const float h1 = z1 * __fdividef(1.0f, 1.0f + __expf(-z1));
+        const float4 w0 = reinterpret_cast<const float4*>(S.bwot)[j], w1 = reinterpret_cast<const float4*>(S.bwot)[j + 1];
+        const f32x2 hh0 = pk2(h0, h0), hh1 = pk2(h1, h1);
+        p01 = fma2(hh0, pk2(w0.x, w0.y), p01); p23 = fma2(hh0, pk2(w0.z, w0.w), p23);
+        p01 = fma2(hh1, pk2(w1.x, w1.y), p01); p23 = fma2(hh1, pk2(w1.z, w1.w), p23);
+    }
+    upk2(p01, p[0], p[1]); upk2(p23, p[2], p[3]);
+}
+
+// Issue one round of MMAs for a group (executed by ONE thread; every operand is warp-uniform).  Each layer's
+// operand image = HI [N x 32] then LO [N x 32] (W = hi + lo): the value path accumulates A.hi^T + A.lo^T,
+// tangents use hi only.  type 0: first layer (tangent seeds are K=16 operands in A_u/A_v chunk 0),
+// 1..NH-1: hidden layer, NH: output layer (N = 16).
 template <bool TANGENTS>
 __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint32_t w_base, uint32_t bar) {
     constexpr uint32_t idesc32 = make_idesc(32), idesc16 = make_idesc(16);
-    if (type == 0) {                                // layer 1: D_z = A1 . W1^T  (K = 32 -> 2 x K16 per image)
-        const uint64_t b = make_b_desc(w_base, 512, 128);
-        mma_ts(tg + kColD, tg + kColA1, b, idesc32, 0u);
-        mma_ts(tg + kColD, tg + kColA1 + 8, b + (1024 >> 4), idesc32, 1u);
-        mma_ts(tg + kColD, tg + kColA1, b + (2048 >> 4), idesc32, 1u);
-        mma_ts(tg + kColD, tg + kColA1 + 8, b + (3072 >> 4), idesc32, 1u);
-    } else if (type < NH) {                         // hidden layer (type+1)
+    if (type < NH) {
         const uint64_t b = make_b_desc(w_base + 4096u * type, 512, 128);
-        mma_ts(tg + kColD, tg + kColA, b, idesc32, 0u);
-        mma_ts(tg + kColD, tg + kColA + 8, b + (1024 >> 4), idesc32, 1u);
-        mma_ts(tg + kColD, tg + kColA, b + (2048 >> 4), idesc32, 1u);
-        mma_ts(tg + kColD, tg + kColA + 8, b + (3072 >> 4), idesc32, 1u);
+        const uint32_t a = tg + (type == 0 ? kColA1 : kColA);
+        mma_ts<0>(tg + kColD, a, b, idesc32);
+        mma_ts<1>(tg + kColD, a + 8, b + (1024 >> 4), idesc32);
+        mma_ts<1>(tg + kColD, a, b + (2048 >> 4), idesc32);
+        mma_ts<1>(tg + kColD, a + 8, b + (3072 >> 4), idesc32);
         if (TANGENTS) {
-#pragma unroll
-            for (int c = 1; c < 3; ++c) {
-                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c, b, idesc32, 0u);
-                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b + (1024 >> 4), idesc32, 1u);
+            mma_ts<0>(tg + kColD + 32, tg + kColA + 16, b, idesc32);
+            mma_ts<0>(tg + kColD + 64, tg + kColA + 32, b, idesc32);
+            if (type != 0) {
+                mma_ts<1>(tg + kColD + 32, tg + kColA + 16 + 8, b + (1024 >> 4), idesc32);
+                mma_ts<1>(tg + kColD + 64, tg + kColA + 32 + 8, b + (1024 >> 4), idesc32);
             }
         }
     } else {                                        // output layer, N = 16
         const uint64_t b = make_b_desc(w_base + 4096u * NH, 256, 128);
-        mma_ts(tg + kColD, tg + kColA, b, idesc16, 0u);
-        mma_ts(tg + kColD, tg + kColA + 8, b + (512 >> 4), idesc16, 1u);
-        mma_ts(tg + kColD, tg + kColA, b + (1024 >> 4), idesc16, 1u);
-        mma_ts(tg + kColD, tg + kColA + 8, b + (1536 >> 4), idesc16, 1u);
+        mma_ts<0>(tg + kColD, tg + kColA, b, idesc16);
+        mma_ts<1>(tg + kColD, tg + kColA + 8, b + (512 >> 4), idesc16);
+        mma_ts<1>(tg + kColD, tg + kColA, b + (1024 >> 4), idesc16);
+        mma_ts<1>(tg + kColD, tg + kColA + 8, b + (1536 >> 4), idesc16);
         if (TANGENTS) {
 #pragma unroll
             for (int c = 1; c < 3; ++c) {
-                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c, b, idesc16, 0u);
-                mma_ts(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b + (512 >> 4), idesc16, 1u);
+                mma_ts<0>(tg + kColD + 32 * c, tg + kColA + 16 * c, b, idesc16);
+                mma_ts<1>(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b + (512 >> 4), idesc16);
             }
         }
     }
     tc_commit(bar);
 }
 
-// Optional in-kernel phase timers (PROF instantiation only, selected with BSDFDIFF_TC_PROFILE=1): cycles per
-// warp spent in  0 prologue/state-pack, 1 waiting for MMA results, 2 tcgen05.ld + activation math + st issue,
-// 3 wait::st + group barrier, 4 MMA issue, 5 output round + epilogue, 6 total.
-constexpr int kProfSlots = 8;
-__device__ unsigned long long g_tc_prof[148 * 12 * kProfSlots];
-#define PROF_T(slot)                                                     \
-    do {                                                                 \
-        if (PROF) {                                                      \
-            const long long now_ = clock64();                            \
-            prof[slot] += (unsigned long long)(now_ - tlast);            \
-            tlast = now_;                                                \
-        }                                                                \
-    } while (0)
+// Hand the freshly written A operands to the tensor core: all 128 threads' TMEM stores must have landed
+// before one elected lane issues the round.
+template <bool TANGENTS>
+__device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH, uint32_t tg_mma, uint32_t w_base,
+                                                  uint32_t bar) {
+    tc_wait_st();
+    tc_fence_before();
+    group_sync(g);
+    if (q == 0) {
+        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS>(type, NH, tg_mma, w_base, bar); }
+    }
+}
 
-template <bool TANGENTS, int ACT, bool PROF>
+template <int DOMAIN, int MODE, int ACT>
 __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams P) {
+    constexpr bool TANGENTS = (MODE != kModeForward);
     __shared__ TcSmem S;
     // warp index through a shuffle so the compiler can prove it warp-uniform: TMEM addresses and MMA
     // descriptors then live in uniform registers (no per-MMA R2UR/ELECT waterfall)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    unsigned long long prof[kProfSlots] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tlast = PROF ? clock64() : 0;
-    const long long tstart = tlast;
     const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.flow);
     const int NH = P.n_hidden;
 
@@ -294,11 +364,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         mbar_expect_tx(smem_u32(&S.w_bar), f16_bytes);
         tma_bulk_g2s(smem_u32(S.w16), P.flow + hdr->off_f16, f16_bytes, smem_u32(&S.w_bar));
     }
-    {
-        const float* aux = reinterpret_cast<const float*>(P.flow + hdr->reserved[0]);
-        if (threadIdx.x < 32)
-            S.aux[threadIdx.x] = make_float4(aux[threadIdx.x], aux[32 + threadIdx.x], aux[64 + threadIdx.x], 0.0f);
-        if (P.base) for (int i = threadIdx.x; i < kBaseFloats; i += kTcThreads) S.base[i] = P.base[i];
+    if (P.base) {
+        for (int i = threadIdx.x; i < kPE3 * 16; i += kTcThreads) {          // w1t[k][j] = W1[j][k]
+            const int k = i >> 4, j = i & 15;
+            S.bw1t[i] = P.base[j * kPE3 + k];
+        }
+        if (threadIdx.x < 16) S.bb1[threadIdx.x] = P.base[224 + threadIdx.x];
+        if (threadIdx.x < 64) {                                              // wot[j][c] = Wo[c][j]
+            const int j = threadIdx.x >> 2, c = threadIdx.x & 3;
+            S.bwot[threadIdx.x] = P.base[240 + c * 16 + j];
+        }
+        if (threadIdx.x < 4) S.bbo[threadIdx.x] = P.base[304 + threadIdx.x];
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -320,13 +396,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     const uint32_t bar_d = smem_u32(&S.d_ready[g]);
     const uint32_t w_base = smem_u32(S.w16);
     uint32_t pd = 0;
-    bool ok = true;
     const float inv_t = (float)(1.0 / (double)P.T);
-    const float sgn = (P.mode == kModePdf) ? -1.0f : 1.0f;
-    const float step = sgn * inv_t;
-    if (q == 0) ok = mbar_wait(smem_u32(&S.w_bar), 0);                      // weights have landed in smem
+    const float step = (MODE == kModePdf) ? -inv_t : inv_t;
+    if (q == 0) mbar_wait(smem_u32(&S.w_bar), 0);                           // weights have landed in smem
 
-    for (long long k = g; k < my_tiles && ok; k += kGroups) {
+    for (long long k = g; k < my_tiles; k += kGroups) {
         const long long tile = blockIdx.x + k * gridDim.x;
         const long long i_raw = tile * kTile + q * 32 + lane;
         const bool valid = i_raw < P.n;
@@ -344,24 +418,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             c[11] = 0u;
             tmem_st8(tg + kColA1 + 4, c);
             tmem_st4(tg + kColA1 + 12, c[8], c[9], c[10], c[11]);
-            if (P.base) {       // base net shares the first three PE frequencies (PE3 is a prefix of PE5)
-                const float* b = S.base;
-                bp[0] = b[304]; bp[1] = b[305]; bp[2] = b[306]; bp[3] = b[307];
-#pragma unroll 4
-                for (int j = 0; j < 16; ++j) {
-                    float z = b[224 + j];
-#pragma unroll
-                    for (int kk = 0; kk < kPE3; ++kk) z = fmaf(e[kk], b[j * kPE3 + kk], z);
-                    const float h = z * __fdividef(1.0f, 1.0f + __expf(-z));
-                    bp[0] = fmaf(h, b[240 + j], bp[0]); bp[1] = fmaf(h, b[256 + j], bp[1]);
-                    bp[2] = fmaf(h, b[272 + j], bp[2]); bp[3] = fmaf(h, b[288 + j], bp[3]);
-                }
-            }
+            if (P.base) base_eval_smem(S, e, bp);           // PE3 is a prefix of PE5
         }
 
         float x0, x1, R = 1.0f, p0 = 1.0f;
         float wox = 0.0f, woy = 0.0f, woz = 1.0f, theta_o = 0.0f;
-        if (P.mode == kModePdf) {
+        if (MODE == kModePdf) {
             load_wo(P, i, x0, x1, wox, woy, woz);
             theta_o = x0;
         } else {
@@ -369,120 +431,74 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 const float2 t = reinterpret_cast<const float2*>(P.x0)[i];
                 x0 = t.x; x1 = t.y;
             } else {
-                base_draw(P.domain, bp, P.seed, P.offset, P.first_index + i, x0, x1);
+                base_draw(DOMAIN, bp, P.seed, P.offset, P.first_index + i, x0, x1);
             }
             if (P.out_x0 && valid) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
-            if (P.mode == kModeSample) p0 = expf(base_logprob(P.domain, bp, x0, x1));
+            if (MODE == kModeSample) p0 = expf(base_logprob(DOMAIN, bp, x0, x1));
         }
 
-        for (int t = 0; t < P.T && ok; ++t) {
+#pragma unroll 1
+        for (int t = 0; t < P.T; ++t) {
             const float tf = (float)t / (float)P.T;
-            const float alpha = (P.mode == kModePdf) ? 1.0f - tf : tf;
-            // ---- state -> A1 columns 0..3 (hi parts, then lo parts) ----
-            float sphi = 0.0f, cphi = 1.0f;
+            const float alpha = (MODE == kModePdf) ? 1.0f - tf : tf;
+            // ---- state -> A1 columns 0..3 (hi parts, then lo parts); tangent seeds -> A_u, A_v chunk 0 ----
             {
                 float s0, s1, s2v, s3;
-                if (P.domain == kDisk) { s0 = x0; s1 = x1; s2v = alpha; s3 = 0.0f; }
-                else { __sincosf(x1, &sphi, &cphi); s0 = x0; s1 = sphi; s2v = cphi; s3 = alpha; }
-                const float h0 = f16_round(s0), h1 = f16_round(s1), h2 = f16_round(s2v), h3 = f16_round(s3);
-                uint32_t c0, c1, c2, c3;
-                if (P.domain == kDisk) {
+                if (DOMAIN == kDisk) { s0 = x0; s1 = x1; s2v = alpha; s3 = 0.0f; }
+                else { __sincosf(x1, &s1, &s2v); s0 = x0; s3 = alpha; }
+                const uint32_t c01 = pack_h2(s0, s1), c23 = pack_h2(s2v, s3);
+                const uint32_t l01 = pack_h2(s0 - h2_lo(c01), s1 - h2_hi(c01));
+                const uint32_t l23 = pack_h2(s2v - h2_lo(c23), s3 - h2_hi(c23));
+                if (DOMAIN == kDisk) {
                     // k: x0_hi x1_hi | a_hi a_lo | x0_lo x1_lo | 0 0
-                    c0 = pack_h2(h0, h1); c1 = pack_h2(h2, s2v - h2); c2 = pack_h2(s0 - h0, s1 - h1); c3 = 0u;
+                    tmem_st4(tg + kColA1, c01, (c23 & 0xffffu) | (l23 << 16), l01, 0u);
+                    if (TANGENTS) {
+                        const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx0: k = 0
+                        const uint32_t ev[8] = {0x3C000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx1: k = 1
+                        tmem_st8(tg + kColA + 16, eu);
+                        tmem_st8(tg + kColA + 32, ev);
+                    }
                 } else {
                     // k: th_hi sin_hi | cos_hi a_hi | th_lo sin_lo | cos_lo a_lo
-                    c0 = pack_h2(h0, h1); c1 = pack_h2(h2, h3); c2 = pack_h2(s0 - h0, s1 - h1);
-                    c3 = pack_h2(s2v - h2, s3 - h3);
-                }
-                tmem_st4(tg + kColA1, c0, c1, c2, c3);
-            }
-            PROF_T(0);
-            tc_wait_st();
-            tc_fence_before();
-            group_sync(g);
-            PROF_T(3);
-            if (q == 0 && elect_one()) { tc_fence_after(); issue_round<TANGENTS>(0, NH, tg_mma, w_base, bar_d); }
-            __syncwarp();
-            PROF_T(4);
-
-            // ---- round 0: first layer ----
-            ok = mbar_wait(bar_d, pd); pd ^= 1u;
-            __syncwarp();
-            PROF_T(1);
-            tc_fence_after();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float z[16];
-                tmem_ld16(tg + kColD + 16 * half, z);
-                tc_wait_ld();
-                uint32_t ph[8], pu[8], pv[8];
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    f32x2 h, s2;
-                    silu_pair2<ACT>(z[j], z[j + 1], h, s2);
-                    ph[j >> 1] = pack_h2(h);
+                    tmem_st4(tg + kColA1, c01, c23, l01, l23);
                     if (TANGENTS) {
-                        const float4 a0 = S.aux[16 * half + j], a1 = S.aux[16 * half + j + 1];
-                        f32x2 su, sv;
-                        su = pk2(a0.x, a1.x);
-                        if (P.domain == kDisk) sv = pk2(a0.y, a1.y);
-                        else sv = pk2(fmaf(cphi, a0.y, -sphi * a0.z), fmaf(cphi, a1.y, -sphi * a1.z));
-                        pu[j >> 1] = pack_h2(mul2(s2, su));
-                        pv[j >> 1] = pack_h2(mul2(s2, sv));
+                        // d/dtheta: k = 0.  d/dphi: d(sin) = cos on k = 1, d(cos) = -sin on k = 2 (hi parts), lo parts
+                        // on k = 5, 6 (the weight image repeats W1[:,1], W1[:,2] there)
+                        const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                        const uint32_t ev[8] = {c23 << 16, (c01 >> 16) ^ 0x8000u, l23 << 16, (l01 >> 16) ^ 0x8000u,
+                                                0u, 0u, 0u, 0u};
+                        tmem_st8(tg + kColA + 16, eu);
+                        tmem_st8(tg + kColA + 32, ev);
                     }
                 }
-                tmem_st8(tg + kColA + 8 * half, ph);
-                if (TANGENTS) { tmem_st8(tg + kColA + 16 + 8 * half, pu); tmem_st8(tg + kColA + 32 + 8 * half, pv); }
             }
-            PROF_T(2);
-            tc_wait_st();
-            tc_fence_before();
-            group_sync(g);
-            PROF_T(3);
-            if (q == 0 && elect_one()) { tc_fence_after(); issue_round<TANGENTS>(1, NH, tg_mma, w_base, bar_d); }
-            __syncwarp();
-            PROF_T(4);
+            publish_and_issue<TANGENTS>(g, q, 0, NH, tg_mma, w_base, bar_d);
 
-            // ---- hidden rounds ----
-            for (int l = 1; l < NH && ok; ++l) {
-                ok = mbar_wait(bar_d, pd); pd ^= 1u;
-                __syncwarp();
-                PROF_T(1);
+            // ---- activation rounds: layer 1 and the hidden layers share one instruction stream ----
+#pragma unroll 1
+            for (int l = 0; l < NH; ++l) {
+                mbar_wait(bar_d, pd); pd ^= 1u;
                 tc_fence_after();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float z[16], du[TANGENTS ? 16 : 1], dv[TANGENTS ? 16 : 1];
-                    tmem_ld16(tg + kColD + 16 * half, z);
-                    if (TANGENTS) { tmem_ld16(tg + kColD + 32 + 16 * half, du); tmem_ld16(tg + kColD + 64 + 16 * half, dv); }
-                    tc_wait_ld();
-                    uint32_t ph[8], pu[8], pv[8];
-#pragma unroll
-                    for (int j = 0; j < 16; j += 2) {
-                        f32x2 h, s2;
-                        silu_pair2<ACT>(z[j], z[j + 1], h, s2);
-                        ph[j >> 1] = pack_h2(h);
-                        if (TANGENTS) {
-                            pu[j >> 1] = pack_h2(mul2(s2, pk2(du[j], du[j + 1])));
-                            pv[j >> 1] = pack_h2(mul2(s2, pk2(dv[j], dv[j + 1])));
-                        }
-                    }
-                    tmem_st8(tg + kColA + 8 * half, ph);
-                    if (TANGENTS) { tmem_st8(tg + kColA + 16 + 8 * half, pu); tmem_st8(tg + kColA + 32 + 8 * half, pv); }
-                }
-                PROF_T(2);
-                tc_wait_st();
-                tc_fence_before();
-                group_sync(g);
-                PROF_T(3);
-                if (q == 0 && elect_one()) { tc_fence_after(); issue_round<TANGENTS>(l + 1, NH, tg_mma, w_base, bar_d); }
-                __syncwarp();
-                PROF_T(4);
+                float za[16], ua[TANGENTS ? 16 : 1], va[TANGENTS ? 16 : 1];
+                float zb[16], ub[TANGENTS ? 16 : 1], vb[TANGENTS ? 16 : 1];
+                tmem_ld16(tg + kColD, za);
+                if (TANGENTS) { tmem_ld16(tg + kColD + 32, ua); tmem_ld16(tg + kColD + 64, va); }
+                tc_wait_ld();
+                tmem_ld16(tg + kColD + 16, zb);            // second half streams in under the first half's math
+                if (TANGENTS) { tmem_ld16(tg + kColD + 32 + 16, ub); tmem_ld16(tg + kColD + 64 + 16, vb); }
+                uint32_t ph[8], pu[8], pv[8];
+                activate16<TANGENTS, ACT>(za, ua, va, ph, pu, pv);
+                tmem_st8(tg + kColA, ph);
+                if (TANGENTS) { tmem_st8(tg + kColA + 16, pu); tmem_st8(tg + kColA + 32, pv); }
+                tc_wait_ld();
+                activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
+                tmem_st8(tg + kColA + 8, ph);
+                if (TANGENTS) { tmem_st8(tg + kColA + 16 + 8, pu); tmem_st8(tg + kColA + 32 + 8, pv); }
+                publish_and_issue<TANGENTS>(g, q, l + 1, NH, tg_mma, w_base, bar_d);
             }
 
             // ---- output round: d, dd/dx0, dd/dx1 ----
-            ok = ok && mbar_wait(bar_d, pd); pd ^= 1u;
-            __syncwarp();
-            PROF_T(1);
+            mbar_wait(bar_d, pd); pd ^= 1u;
             tc_fence_after();
             float d0, d1, du0 = 0.f, du1 = 0.f, dv0 = 0.f, dv1 = 0.f;
             tmem_ld2(tg + kColD, d0, d1);
@@ -492,27 +508,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 const float j00 = fmaf(step, du0, 1.0f), j01 = step * dv0;
                 const float j10 = step * du1, j11 = fmaf(step, dv1, 1.0f);
                 const float det = j00 * j11 - j01 * j10;
-                R = (P.mode == kModePdf) ? R * det : R / det;
+                R = (MODE == kModePdf) ? R * det : __fdividef(R, det);
             }
             x0 = fmaf(step, d0, x0);
             x1 = fmaf(step, d1, x1);
-            PROF_T(5);
         }
 
-        if (valid && ok) {
-            if (P.mode == kModeSample) {
+        if (valid) {
+            if (MODE == kModeSample) {
                 store_sample(P, i, x0, x1, p0 * R);
-            } else if (P.mode == kModePdf) {
-                store_pdf(P, i, expf(base_logprob(P.domain, bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
+            } else if (MODE == kModePdf) {
+                store_pdf(P, i, expf(base_logprob(DOMAIN, bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
             } else {
                 reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
             }
         }
-        PROF_T(5);
-    }
-    if (PROF && lane == 0 && blockIdx.x < 148) {
-        prof[6] = (unsigned long long)(clock64() - tstart);
-        for (int s = 0; s < kProfSlots; ++s) g_tc_prof[(blockIdx.x * 12 + warp) * kProfSlots + s] = prof[s];
     }
 
     // ---- teardown ---------------------------------------------------------------------------------
@@ -525,7 +535,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     }
 }
 
-template <bool TANGENTS, int ACT>
+template <int DOMAIN, int MODE, int ACT>
 static int launch_tc_t(const FlowParams& P, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -534,34 +544,31 @@ static int launch_tc_t(const FlowParams& P, cudaStream_t stream) {
     long long grid = sms;
     if (grid > tiles) grid = tiles;
     if (grid < 1) return 0;
-    static const bool profile = (getenv("BSDFDIFF_TC_PROFILE") != nullptr);    // bring-up / tuning aid only
-    if (profile && TANGENTS && ACT == 1)
-        flow_tc_kernel<TANGENTS, ACT, true><<<(unsigned)grid, kTcThreads, 0, stream>>>(P);
-    else
-        flow_tc_kernel<TANGENTS, ACT, false><<<(unsigned)grid, kTcThreads, 0, stream>>>(P);
+    flow_tc_kernel<DOMAIN, MODE, ACT><<<(unsigned)grid, kTcThreads, 0, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
+template <int DOMAIN, int ACT>
+static int launch_tc_m(const FlowParams& P, cudaStream_t stream) {
+    switch (P.mode) {
+        case kModeSample: return launch_tc_t<DOMAIN, kModeSample, ACT>(P, stream);
+        case kModePdf: return launch_tc_t<DOMAIN, kModePdf, ACT>(P, stream);
+        default: return launch_tc_t<DOMAIN, kModeForward, ACT>(P, stream);
+    }
 }
 
 // variant 1 = tc16 (tanh.approx activation), 2 = tc16 with fp32 exp-form activation (cross-check)
 int launch_tc(const FlowParams& P, cudaStream_t stream, int variant) {
     if (P.hidden != 32 || P.n_hidden < 2 || P.n_hidden > 6) return -2;      // 64-wide nets: CUDA-core path
-    const bool tang = (P.mode != kModeForward);
-    if (variant == 2) return tang ? launch_tc_t<true, 0>(P, stream) : launch_tc_t<false, 0>(P, stream);
-    return tang ? launch_tc_t<true, 1>(P, stream) : launch_tc_t<false, 1>(P, stream);
+    if (P.domain == kDisk)
+        return variant == 2 ? launch_tc_m<kDisk, 0>(P, stream) : launch_tc_m<kDisk, 1>(P, stream);
+    return variant == 2 ? launch_tc_m<kSpherical, 0>(P, stream) : launch_tc_m<kSpherical, 1>(P, stream);
 }
 
 unsigned int tc_timeout_flag() {
     unsigned int v = 0;
     cudaMemcpyFromSymbol(&v, g_tc_timeout_flag, sizeof(v));
     return v;
-}
-
-// copies the phase timers of the last profiled launch: [148 CTAs][12 warps][8 slots] cycles (synchronises)
-int tc_profile_fetch(unsigned long long* out, int max_elems) {
-    const int n = 148 * 12 * kProfSlots;
-    if (max_elems < n) return -1;
-    cudaDeviceSynchronize();
-    return cudaMemcpyFromSymbol(out, g_tc_prof, sizeof(unsigned long long) * n) == cudaSuccess ? n : -3;
 }
 
 }  // namespace bsdfdiff

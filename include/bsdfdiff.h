@@ -69,9 +69,6 @@ int         bsdfdiff_abi_version(void);
 const char* bsdfdiff_error_string(int code);
 int         bsdfdiff_last_cuda_error(void);          /* cudaError_t of the last failure on this thread */
 int         bsdfdiff_debug_timeout_flag(void);       /* 1 if a tensor-core kernel ever hit its mbarrier watchdog (syncs) */
-/* Tuning aid: with BSDFDIFF_TC_PROFILE=1 in the environment the tensor-core kernel accumulates per-warp phase
- * timers; this copies them out as [148 CTAs][12 warps][8 slots] cycle counts (synchronises the device). */
-int         bsdfdiff_debug_profile_fetch(unsigned long long* out /*host*/, int max_elems);
 
 /* ---- weight packing (host side; the blob is then copied to the device by the caller) ------------------------
  * Flow net = bias-free MLP, layers given as row-major [rows,cols] fp32 matrices exactly as the checkpoints
