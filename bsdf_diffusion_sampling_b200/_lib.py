@@ -10,7 +10,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbsdfdiff.so")
+LIB_PATH = os.environ.get("BSDFDIFF_LIB") or os.path.join(HERE, "libbsdfdiff.so")   # env override: tuning builds only
 
 # constants mirrored from include/bsdfdiff.h
 DISK, SPHERICAL = 0, 1

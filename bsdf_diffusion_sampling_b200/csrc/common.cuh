@@ -260,6 +260,7 @@ __device__ __forceinline__ void load_wo(const FlowParams& P, long long i, float&
 
 // Final mapping for sample(): domain state -> outgoing direction + solid-angle pdf (tensor part of
 // MyBSDF.sample before the ground-truth firefly clamp).
+template <bool FAST = false>   // FAST: MUFU sin/cos (tensor-core path; ~1e-6 abs on wo)
 __device__ __forceinline__ void store_sample(const FlowParams& P, long long i, float x0, float x1, float pdf) {
     if (P.epilogue == kEpiRaw) {
         reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
@@ -275,8 +276,8 @@ __device__ __forceinline__ void store_sample(const FlowParams& P, long long i, f
         pdf = pdf * oz;
     } else {                                                        // brdf_measured_spherical.py:79-92
         float st, ct, sp, cp;
-        sincosf(x0, &st, &ct);
-        sincosf(x1, &sp, &cp);
+        if (FAST) { __sincosf(x0, &st, &ct); __sincosf(x1, &sp, &cp); }
+        else { sincosf(x0, &st, &ct); sincosf(x1, &sp, &cp); }
         if (!(st > 0.00005f)) pdf = 0.0f;
         if (P.epilogue == kEpiSpherical && !(ct > 0.0f)) pdf = 0.0f;
         ox = cp * st; oy = sp * st; oz = ct;                        // sph_to_dir :31-34
@@ -287,12 +288,13 @@ __device__ __forceinline__ void store_sample(const FlowParams& P, long long i, f
 }
 
 // Final masks / Jacobian for pdf() (tensor part of MyBSDF.pdf).
+template <bool FAST = false>
 __device__ __forceinline__ void store_pdf(const FlowParams& P, long long i, float pdf, float wiz,
                                           float wox, float woy, float woz, float theta_o) {
     if (P.epilogue == kEpiDisk) {                                   // brdf_measured_disk.py:122-124
         pdf = (wiz > 0.0f && woz > 0.0f) ? pdf * woz : 0.0f;
     } else if (P.epilogue == kEpiSpherical) {                       // brdf_measured_spherical.py:134-137
-        if (!(sinf(theta_o) > 0.00005f)) pdf = 0.0f;
+        if (!((FAST ? __sinf(theta_o) : sinf(theta_o)) > 0.00005f)) pdf = 0.0f;
         pdf = (wiz > 0.0f && woz > 0.0f) ? pdf * inv_sin_clamped(wox, woy) : 0.0f;
     } else if (P.epilogue == kEpiBsdf) {                            // bsdf_myresult.py:121-130
         pdf = pdf * inv_sin_clamped(wox, woy);

@@ -49,7 +49,10 @@
 
 namespace bsdfdiff {
 
-constexpr int kGroups = 3;
+#ifndef BSDFDIFF_TC_GROUPS
+#define BSDFDIFF_TC_GROUPS 3      // tuning builds only: 1 or 2 groups isolate the per-round latency chain
+#endif
+constexpr int kGroups = BSDFDIFF_TC_GROUPS;
 constexpr int kTcThreads = kGroups * 128;
 constexpr int kTile = 128;
 constexpr int kColsPerGroup = 160;
@@ -69,28 +72,27 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ unsigned int g_tc_timeout_flag = 0;
 
-__device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(bar), "r"(parity), "r"(20000u) : "memory");
-    return done;
-}
-// Watchdog path (never taken by a correct protocol): keep polling for a bounded time, then record the fault and
-// abort the launch -- a protocol bug must never hang the GPU.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
-#pragma unroll 1
-    for (int it = 0; it < (1 << 20); ++it)
-        if (mbar_try(bar, parity)) return;
-    atomicExch(&g_tc_timeout_flag, 1u);
-    __trap();
-}
-// try_wait suspends the warp in hardware (up to the hint) instead of spinning, so waiting warps do not steal
-// issue slots from the computing ones; the first probe almost always succeeds.
+// Wait for the phase with the given parity.  try_wait suspends the warp in hardware (up to the hint) instead of
+// spinning, so waiting warps do not steal issue slots from the computing ones.  The loop is bounded: a protocol
+// bug records the fault and aborts the launch instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0x400000;\n"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "sub.u32 n, n, 1;\n\t"
+        "setp.ne.u32 p, n, 0;\n\t"
+        "@p bra WAIT_%=;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "bra END_%=;\n"
+        "DONE_%=:\n\t"
+        "mov.u32 %0, 1;\n"
+        "END_%=:\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+    if (!ok) { atomicExch(&g_tc_timeout_flag, 1u); __trap(); }
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -244,6 +246,73 @@ __device__ __forceinline__ void pe5_fast(float v0, float v1, float* e) {
         c0 = fmaf(c0, c0, -s0 * s0); c1 = fmaf(c1, c1, -s1 * s1);
         s0 = ns0; s1 = ns1;
     }
+}
+
+// ---- base distribution with MUFU-grade intrinsics (the tensor-core path tolerates ~1e-6 relative here; the
+// fp32 parity path keeps the precise versions in common.cuh).  Same formulas as base_draw / base_logprob.
+__device__ __forceinline__ float softplus_fast(float x) { return x > 20.0f ? x : __logf(1.0f + __expf(x)); }
+__device__ __forceinline__ float log_i0_fast(float x) {
+    if (x < 3.75f) {
+        float y = x * (1.0f / 3.75f); y = y * y;
+        float r = 0.45813e-2f;
+        r = fmaf(y, r, 0.360768e-1f); r = fmaf(y, r, 0.2659732f); r = fmaf(y, r, 1.2067492f);
+        r = fmaf(y, r, 3.0899424f);   r = fmaf(y, r, 3.5156229f); r = fmaf(y, r, 1.0f);
+        return __logf(r);
+    }
+    float y = __fdividef(3.75f, x);
+    float r = 0.392377e-2f;
+    r = fmaf(y, r, -0.1647633e-1f); r = fmaf(y, r, 0.2635537e-1f); r = fmaf(y, r, -0.2057706e-1f);
+    r = fmaf(y, r, 0.916281e-2f);   r = fmaf(y, r, -0.157565e-2f); r = fmaf(y, r, 0.225319e-2f);
+    r = fmaf(y, r, 0.1328592e-1f);  r = fmaf(y, r, 0.39894228f);
+    return x - 0.5f * __logf(x) + __logf(r);
+}
+template <int DOMAIN>
+__device__ __forceinline__ float base_logprob_fast(const float p[4], float x0, float x1) {
+    if (DOMAIN == kDisk) {
+        const float e0 = (x0 - p[0]) * __expf(-p[2]), e1 = (x1 - p[1]) * __expf(-p[3]);
+        return -kLog2Pi - (p[2] + p[3]) - 0.5f * (e0 * e0 + e1 * e1);
+    }
+    const float kappa = softplus_fast(p[3]) + 1e-3f;
+    const float e = __fdividef(x0 - p[0], __expf(p[1]) + 1e-3f);
+    const float loggau = -0.5f * kLog2Pi - p[1] - 0.5f * e * e;
+    const float logvon = kappa * __cosf(x1 - p[2]) - kLog2Pi - log_i0_fast(kappa);
+    return loggau + logvon;
+}
+template <int DOMAIN>
+__device__ __forceinline__ void base_draw_fast(const float p[4], unsigned long long seed, unsigned long long offset,
+                                               long long index, float& x0, float& x1) {
+    const uint4 r4 = philox_draw(seed, offset, index, 0);
+    float n0, n1;
+    {
+        const float r = sqrtf(-2.0f * __logf(u01(r4.x)));
+        float s, c;
+        __sincosf(6.283185307179586f * u01(r4.y) - 3.141592653589793f, &s, &c);   // argument in (-pi, pi)
+        n0 = -r * c; n1 = -r * s;
+    }
+    if (DOMAIN == kDisk) {
+        x0 = fmaf(n0, __expf(p[2]), p[0]);
+        x1 = fmaf(n1, __expf(p[3]), p[1]);
+        return;
+    }
+    x0 = fmaf(n0, __expf(p[1]) + 1e-3f, p[0]);
+    const float kappa = softplus_fast(p[3]) + 1e-3f, mu = p[2];
+    const float s = sqrtf(fmaf(4.0f * kappa, kappa, 1.0f));
+    const float tau = 1.0f + s;
+    const float rho = __fdividef(tau * 2.0f * kappa, (s + 1.0f) * (tau + sqrtf(2.0f * tau)));
+    const float r = __fdividef(1.0f + rho * rho, 2.0f * rho);
+    float phi = 0.0f;
+    for (uint32_t round = 1; round <= 64; ++round) {                // acceptance >= ~0.66 per round
+        const uint4 q = philox_draw(seed, offset, index, round);
+        const float z = __cosf(3.141592653589793f * u01(q.x));
+        const float f = __fdividef(1.0f + r * z, r + z);
+        const float cc = kappa * (r - f);
+        const float u2 = u01(q.y);
+        phi = ((q.z & 0x80000000u) ? 1.0f : -1.0f) * acosf(fminf(fmaxf(f, -1.0f), 1.0f));
+        if ((cc * (2.0f - cc) - u2 > 0.0f) || (__logf(__fdividef(cc, u2)) + 1.0f - cc >= 0.0f)) break;
+    }
+    float y = phi + 3.14159265358979f + mu;
+    y = y - 6.28318530717959f * floorf(y * 0.159154943091895f);   // python-style modulo
+    x1 = y - 3.14159265358979f;
 }
 
 struct TcSmem {
@@ -431,10 +500,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 const float2 t = reinterpret_cast<const float2*>(P.x0)[i];
                 x0 = t.x; x1 = t.y;
             } else {
-                base_draw(DOMAIN, bp, P.seed, P.offset, P.first_index + i, x0, x1);
+                base_draw_fast<DOMAIN>(bp, P.seed, P.offset, P.first_index + i, x0, x1);
             }
             if (P.out_x0 && valid) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
-            if (MODE == kModeSample) p0 = expf(base_logprob(DOMAIN, bp, x0, x1));
+            if (MODE == kModeSample) p0 = __expf(base_logprob_fast<DOMAIN>(bp, x0, x1));
         }
 
 #pragma unroll 1
@@ -516,9 +585,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
         if (valid) {
             if (MODE == kModeSample) {
-                store_sample(P, i, x0, x1, p0 * R);
+                store_sample<true>(P, i, x0, x1, p0 * R);
             } else if (MODE == kModePdf) {
-                store_pdf(P, i, expf(base_logprob(DOMAIN, bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
+                store_pdf<true>(P, i, __expf(base_logprob_fast<DOMAIN>(bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
             } else {
                 reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
             }

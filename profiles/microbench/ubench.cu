@@ -117,6 +117,175 @@ __device__ __forceinline__ long long pipe_probe(int lane, uint32_t& sink) {
     return t1 - t0;
 }
 
+// activation math on registers only (no TMEM): 8 independent neuron pairs per iteration.
+//   F32: 2 tanh.f32 + fma2, add2, sub2, fma2, mul2 x2 + 3 cvt.f16x2 per pair   (the tc16 inner loop)
+//   H2 : 1 tanh.f16x2 + 6 half2 ops per pair                                  (fp16-accumulator variant)
+template <bool H2>
+__device__ __forceinline__ long long math_probe(int lane, uint32_t& sink) {
+    long long t0, t1;
+    if (!H2) {
+        float z[16], du[16], dv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { z[i] = 0.01f * (lane + i); du[i] = 0.5f + i; dv[i] = 0.25f * i; }
+        uint32_t acc = 0;
+        t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < 256; ++it) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+                float t0f, t1f;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0f) : "f"(z[j]));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1f) : "f"(z[j + 1]));
+                unsigned long long zz, tt, one, h, s2, a, b, u, v, duu, dvv;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(zz) : "f"(z[j]), "f"(z[j + 1]));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(tt) : "f"(t0f), "f"(t1f));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(one) : "f"(1.0f), "f"(1.0f));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(duu) : "f"(du[j]), "f"(du[j + 1]));
+                asm("mov.b64 %0, {%1, %2};" : "=l"(dvv) : "f"(dv[j]), "f"(dv[j + 1]));
+                asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(h) : "l"(zz), "l"(tt));
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(one), "l"(tt));
+                asm("add.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(one), "l"(tt));
+                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(s2) : "l"(h), "l"(a), "l"(b));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(s2), "l"(duu));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(s2), "l"(dvv));
+                float lo, hi; uint32_t ph, pu, pv;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(h));
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph) : "f"(hi), "f"(lo));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(u));
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pu) : "f"(hi), "f"(lo));
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+                asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pv) : "f"(hi), "f"(lo));
+                const uint32_t m = (ph ^ pu ^ pv) & 1u;                  // loop-carried dependency (2 ALU ops + 1)
+                z[j] = __uint_as_float(__float_as_uint(z[j]) ^ m);
+                acc += m;
+            }
+        }
+        t1 = clock64();
+        sink += acc;
+    } else {
+        uint32_t z[8], du[8], dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { z[i] = 0x30003000u + lane + i; du[i] = 0x38003800u + i; dv[i] = 0x34003400u + i; }
+        uint32_t acc = 0;
+        const uint32_t one = 0x3c003c00u;
+        t0 = clock64();
+#pragma unroll 1
+        for (int it = 0; it < 256; ++it) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                uint32_t t, h, a, b, s2, u, v;
+                asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(z[j]));
+                asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h) : "r"(z[j]), "r"(t));
+                asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(a) : "r"(one), "r"(t));
+                asm("add.rn.f16x2 %0, %1, %2;" : "=r"(b) : "r"(one), "r"(t));
+                asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(s2) : "r"(h), "r"(a), "r"(b));
+                asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(u) : "r"(s2), "r"(du[j]));
+                asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(v) : "r"(s2), "r"(dv[j]));
+                const uint32_t m = (h ^ u ^ v) & 1u;
+                z[j] ^= m;
+                acc += m;
+            }
+        }
+        t1 = clock64();
+        sink += acc;
+    }
+    return t1 - t0;
+}
+
+// Alternative formulations of the activation inner loop on registers only (8 neuron pairs per iteration; the only
+// extra work is 2 LOP3 per pair that feed the outputs back into z so nothing is hoisted):
+//   0 f32x2 (shipping)   1 scalar fp32   2 f32 tanh + f32x2 h, half2 s2 and tangent products
+//   3 f32x2 h and s2, tangent products in half2 (du, dv as packed halves: fp16 tangent accumulators)
+//   4 all half2 (fp16 accumulators everywhere)
+template <int V>
+__device__ __forceinline__ long long form_probe(int lane, uint32_t& sink) {
+    float z[16], du[16], dv[16];
+    uint32_t duh[8], dvh[8];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { z[i] = 0.01f * (lane + i); du[i] = 0.5f + i; dv[i] = 0.25f * i; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { duh[i] = 0x38003800u + i; dvh[i] = 0x34003400u + i; }
+    const uint32_t oneh = 0x3c003c00u;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+            uint32_t ph, pu, pv;
+            if (V == 4) {
+                uint32_t zz = __float_as_uint(z[j]), t, h, a, b, s2;
+                asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(zz));
+                asm("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(h) : "r"(zz), "r"(t));
+                asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(a) : "r"(oneh), "r"(t));
+                asm("add.rn.f16x2 %0, %1, %2;" : "=r"(b) : "r"(oneh), "r"(t));
+                asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(s2) : "r"(h), "r"(a), "r"(b));
+                asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pu) : "r"(s2), "r"(duh[j >> 1]));
+                asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pv) : "r"(s2), "r"(dvh[j >> 1]));
+                ph = h;
+            } else {
+                float t0f, t1f;
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t0f) : "f"(z[j]));
+                asm("tanh.approx.f32 %0, %1;" : "=f"(t1f) : "f"(z[j + 1]));
+                if (V == 1) {
+                    const float h0 = fmaf(z[j], t0f, z[j]), h1 = fmaf(z[j + 1], t1f, z[j + 1]);
+                    const float s0 = fmaf(h0, 1.0f - t0f, 1.0f + t0f), s1 = fmaf(h1, 1.0f - t1f, 1.0f + t1f);
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph) : "f"(h1), "f"(h0));
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pu) : "f"(s1 * du[j + 1]), "f"(s0 * du[j]));
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pv) : "f"(s1 * dv[j + 1]), "f"(s0 * dv[j]));
+                } else {
+                    unsigned long long zz, tt, h;
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(zz) : "f"(z[j]), "f"(z[j + 1]));
+                    asm("mov.b64 %0, {%1, %2};" : "=l"(tt) : "f"(t0f), "f"(t1f));
+                    asm("fma.rn.f32x2 %0, %1, %2, %1;" : "=l"(h) : "l"(zz), "l"(tt));
+                    float lo, hi;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(h));
+                    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(ph) : "f"(hi), "f"(lo));
+                    if (V == 2) {
+                        uint32_t th, a, b, s2;
+                        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(th) : "f"(t1f), "f"(t0f));
+                        asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(a) : "r"(oneh), "r"(th));
+                        asm("add.rn.f16x2 %0, %1, %2;" : "=r"(b) : "r"(oneh), "r"(th));
+                        asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(s2) : "r"(ph), "r"(a), "r"(b));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pu) : "r"(s2), "r"(duh[j >> 1]));
+                        asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pv) : "r"(s2), "r"(dvh[j >> 1]));
+                    } else {
+                        unsigned long long one, a, b, s2;
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(one) : "f"(1.0f), "f"(1.0f));
+                        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(a) : "l"(one), "l"(tt));
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(b) : "l"(one), "l"(tt));
+                        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(s2) : "l"(h), "l"(a), "l"(b));
+                        if (V == 0) {
+                            unsigned long long duu, dvv, u, v;
+                            asm("mov.b64 %0, {%1, %2};" : "=l"(duu) : "f"(du[j]), "f"(du[j + 1]));
+                            asm("mov.b64 %0, {%1, %2};" : "=l"(dvv) : "f"(dv[j]), "f"(dv[j + 1]));
+                            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u) : "l"(s2), "l"(duu));
+                            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(v) : "l"(s2), "l"(dvv));
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(u));
+                            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pu) : "f"(hi), "f"(lo));
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+                            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pv) : "f"(hi), "f"(lo));
+                        } else {   // V == 3
+                            uint32_t s2h;
+                            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(s2));
+                            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(s2h) : "f"(hi), "f"(lo));
+                            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pu) : "r"(s2h), "r"(duh[j >> 1]));
+                            asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(pv) : "r"(s2h), "r"(dvh[j >> 1]));
+                        }
+                    }
+                }
+            }
+            uint32_t m;
+            asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(m) : "r"(ph), "r"(pu), "r"(pv));                      // xor3
+            asm("lop3.b32 %0, %1, %2, 1, 0x6a;" : "=r"(m) : "r"(__float_as_uint(z[j])), "r"(m));              // z ^ (m & 1)
+            z[j] = __uint_as_float(m);
+        }
+    }
+    const long long t1 = clock64();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) sink += __float_as_uint(z[i]);
+    return t1 - t0;
+}
+
 struct Res { long long cyc[16]; };
 
 // test ids
@@ -386,7 +555,14 @@ __global__ void __launch_bounds__(512, 1) ubench(int test, int nwarps, int kpara
             case 11: t1 = pipe_probe<8, 8, 8, 0, 0>(lane, sink); break;  // tanh + cvt + fma2
             case 12: t1 = pipe_probe<4, 6, 8, 0, 0>(lane, sink); break;  // the activation mix: 2 tanh : 3 cvt : 4(of 6) fma2
             case 13: t1 = pipe_probe<0, 8, 0, 0, 8>(lane, sink); break;  // cvt + prmt
-            default: t1 = pipe_probe<8, 0, 0, 0, 8>(lane, sink); break;  // tanh + prmt
+            case 14: t1 = pipe_probe<8, 0, 0, 0, 8>(lane, sink); break;  // tanh + prmt
+            case 15: t1 = math_probe<false>(lane, sink); break;
+            case 16: t1 = math_probe<true>(lane, sink); break;
+            case 17: t1 = form_probe<0>(lane, sink); break;
+            case 18: t1 = form_probe<1>(lane, sink); break;
+            case 19: t1 = form_probe<2>(lane, sink); break;
+            case 20: t1 = form_probe<3>(lane, sink); break;
+            default: t1 = form_probe<4>(lane, sink); break;
         }
     }
     if (lane == 0 && warp < 16 && test != T_MMA) out[blockIdx.x].cyc[warp] = (t1 - t0);
@@ -499,10 +675,10 @@ int main() {
         for (int w : {1, 4, 8, 12, 16}) run("cvt.f16x2", T_PACK, w, 0, grid, 16 * 32.0, "cvt-instr-lanes");
         for (int w : {4, 8, 12, 16}) run("act-mix", T_MIX, w, 0, grid, 16 * 32.0, "activations");
         {
-            const char* names[15] = {"tanh x8", "cvt x8", "fma2 x8", "hfma2 x8", "prmt x8", "tanh8+cvt8", "tanh8+fma2_8", "cvt8+fma2_8",
+            const char* names[22] = {"tanh x8", "cvt x8", "fma2 x8", "hfma2 x8", "prmt x8", "tanh8+cvt8", "tanh8+fma2_8", "cvt8+fma2_8",
                                      "tanh8+hfma2_8", "cvt8+hfma2_8", "fma2_8+hfma2_8", "tanh8+cvt8+fma2_8", "tanh4+cvt6+fma2_8",
-                                     "cvt8+prmt8", "tanh8+prmt8"};
-            for (int c = 0; c < 15; ++c) for (int w : {8, 16}) run(names[c], T_TANH_PACK, w, c, grid, 1.0, "(per-thread inner iterations x warps)/clk");
+                                     "cvt8+prmt8", "tanh8+prmt8", "act-math f32x2 (16 act)", "act-math half2 (16 act)", "form0 f32x2", "form1 scalar f32", "form2 half2 tail", "form3 half2 tangent product", "form4 all half2"};
+            for (int c = 15; c < 22; ++c) for (int w : {4, 8, 12, 16}) run(names[c], T_TANH_PACK, w, c, grid, 1.0, "(per-thread inner iterations x warps)/clk");
         }
         for (int k : {1, 2, 3, 6, 8, 12}) run("mma", T_MMA, 1, k, grid, 0, "");
         for (int w : {4, 8, 12}) for (int k : {6, 8}) run("chain", T_CHAIN, w, k, grid, 1.0, "rounds");
