@@ -53,7 +53,19 @@ namespace bsdfdiff {
 #define BSDFDIFF_TC_GROUPS 3      // tuning builds only: 1 or 2 groups isolate the per-round latency chain
 #endif
 constexpr int kGroups = BSDFDIFF_TC_GROUPS;
-constexpr int kTcThreads = kGroups * 128;
+constexpr int kWorkerThreads = kGroups * 128;
+constexpr int kProducerWarps = 4;                  // one 128-thread producer group: thread <-> query row of a tile
+constexpr int kTcThreads = kWorkerThreads + 32 * kProducerWarps;
+constexpr int kSlots = kGroups + 1;                // prologue ring: the producer runs one tile ahead of the groups
+// per-query record handed from the producer to the worker thread of the same row (field-major in shared memory,
+// slot[field][row], so both sides access consecutive words)
+constexpr int kFPe = 0;                            // 11 words: PE5(wi) as packed fp16 pairs (A1 columns 4..14)
+constexpr int kFX = 11;                            // x0, x1: start state (base sample, replayed noise, or wo)
+constexpr int kFP0 = 13;                           // base density at the start state (sample mode)
+constexpr int kFBp = 14;                           // 4 base-net outputs (pdf mode evaluates the base density at the end)
+constexpr int kFWiz = 18;                          // wi_z, wo (pdf-mode masks)
+constexpr int kFWo = 19;
+constexpr int kFields = 22;
 constexpr int kTile = 128;
 constexpr int kColsPerGroup = 160;
 constexpr int kColD = 0, kColA = 96, kColA1 = 144;
@@ -72,27 +84,51 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ unsigned int g_tc_timeout_flag = 0;
 
-// Wait for the phase with the given parity.  try_wait suspends the warp in hardware (up to the hint) instead of
-// spinning, so waiting warps do not steal issue slots from the computing ones.  The loop is bounded: a protocol
-// bug records the fault and aborts the launch instead of hanging the GPU.
+// Wait for the phase with the given parity.  try_wait suspends the warp in hardware instead of spinning, but it
+// also wakes on unrelated mbarrier traffic of the CTA; BACKOFF_NS > 0 (the producer, which runs a whole tile ahead)
+// adds a nanosleep between probes so a long wait does not burn issue slots of the computing warps.  The loop is
+// bounded: a protocol bug records the fault and aborts the launch instead of hanging the GPU.
+template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
-        "mov.u32 n, 0x400000;\n"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "sub.u32 n, n, 1;\n\t"
-        "setp.ne.u32 p, n, 0;\n\t"
-        "@p bra WAIT_%=;\n\t"
-        "mov.u32 %0, 0;\n\t"
-        "bra END_%=;\n"
-        "DONE_%=:\n\t"
-        "mov.u32 %0, 1;\n"
-        "END_%=:\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+    if (BACKOFF_NS > 0) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+            "mov.u32 n, 0x400000;\n"
+            "WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "@p bra DONE_%=;\n\t"
+            "nanosleep.u32 %4;\n\t"
+            "sub.u32 n, n, 1;\n\t"
+            "setp.ne.u32 p, n, 0;\n\t"
+            "@p bra WAIT_%=;\n\t"
+            "mov.u32 %0, 0;\n\t"
+            "bra END_%=;\n"
+            "DONE_%=:\n\t"
+            "mov.u32 %0, 1;\n"
+            "END_%=:\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u), "n"(BACKOFF_NS) : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+            "mov.u32 n, 0x400000;\n"
+            "WAIT_%=:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "@p bra DONE_%=;\n\t"
+            "sub.u32 n, n, 1;\n\t"
+            "setp.ne.u32 p, n, 0;\n\t"
+            "@p bra WAIT_%=;\n\t"
+            "mov.u32 %0, 0;\n\t"
+            "bra END_%=;\n"
+            "DONE_%=:\n\t"
+            "mov.u32 %0, 1;\n"
+            "END_%=:\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+    }
     if (!ok) { atomicExch(&g_tc_timeout_flag, 1u); __trap(); }
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -318,6 +354,8 @@ __device__ __forceinline__ void base_draw_fast(const float p[4], unsigned long l
 struct TcSmem {
     unsigned long long d_ready[kGroups];
     unsigned long long w_bar;
+    unsigned long long full[kSlots];          // producer -> worker group: the slot's records are written
+    unsigned long long empty[kSlots];         // worker group -> producer: the slot has been read
     uint32_t tmem_base;
     uint32_t pad[3];
     // base net re-laid for 128-bit broadcast loads: w1t[k][j] (k < 14, j < 16), b1[16], wot[j][c] (c < 4), bo[4]
@@ -326,6 +364,7 @@ struct TcSmem {
     __align__(16) float bwot[16 * 4];
     __align__(16) float bbo[4];
     __align__(128) unsigned char w16[2 * (32 * 32 + 5 * 32 * 32 + 16 * 32) * 2];   // hi+lo images, <= 6 hidden layers
+    __align__(16) float slot[kSlots][kFields][kTile];
 };
 
 // base net p = Wo silu(W1 PE3(e) + b1) + bo from the shared-memory copy (rendering/utils/model.py:382-386)
@@ -414,10 +453,51 @@ __device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH
     }
 }
 
+// Raw per-query inputs of one tile row, loaded one tile ahead by the producer so the global-load latency is
+// never on anybody's critical path.
+struct RawIn {
+    float wa, wb, wc;        // wi: (w0, w1, -) raw epilogue, or the 3 local-frame components
+    float oa, ob, oc;        // wo (pdf mode)
+    float r0, r1;            // replayed base sample
+};
+template <int MODE>
+__device__ __forceinline__ void raw_load(const FlowParams& P, long long i, RawIn& r) {
+    const long long qi = (P.wi_repeat > 1) ? i / P.wi_repeat : i;
+    if (P.epilogue == kEpiRaw) {
+        const float2 w = reinterpret_cast<const float2*>(P.wi)[qi];
+        r.wa = w.x; r.wb = w.y; r.wc = 1.0f;
+    } else {
+        r.wa = P.wi[3 * qi]; r.wb = P.wi[3 * qi + 1]; r.wc = P.wi[3 * qi + 2];
+    }
+    if (MODE == kModePdf) {
+        if (P.epilogue == kEpiRaw) {
+            const float2 w = reinterpret_cast<const float2*>(P.wo)[i];
+            r.oa = w.x; r.ob = w.y; r.oc = 1.0f;
+        } else {
+            r.oa = P.wo[3 * i]; r.ob = P.wo[3 * i + 1]; r.oc = P.wo[3 * i + 2];
+        }
+    } else if (P.x0) {
+        const float2 t = reinterpret_cast<const float2*>(P.x0)[i];
+        r.r0 = t.x; r.r1 = t.y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernel.  Warp roles (one persistent CTA per SM, 16 warps):
+//   warps 0..11   three worker groups of 4 warps; thread <-> TMEM lane <-> query row of the group's current tile.
+//                 They run nothing but the T-step flow: activation math between tensor-core round trips.
+//   warps 12..15  the producer group; thread <-> query row.  It runs one tile ahead of the workers and does all
+//                 per-query set-up that needs no tensor core: wi (and wo / replayed noise) loads, PE5(wi), the
+//                 base net, the Philox base sample and its density.  Records go through a shared-memory ring
+//                 (full/empty mbarriers).  This work is latency-bound (global loads, 10 serial Philox rounds,
+//                 serial FMA chains); on its own warps it fills the issue slots the workers leave idle while they
+//                 wait for MMAs instead of adding ~1/3 to every tile's critical path (profiles/r1d vs r1h).
+// ------------------------------------------------------------------------------------------------
 template <int DOMAIN, int MODE, int ACT>
 __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams P) {
     constexpr bool TANGENTS = (MODE != kModeForward);
-    __shared__ TcSmem S;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     // warp index through a shuffle so the compiler can prove it warp-uniform: TMEM addresses and MMA
     // descriptors then live in uniform registers (no per-MMA R2UR/ELECT waterfall)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -427,6 +507,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     // ---- one-time setup ---------------------------------------------------------------------------
     if (threadIdx.x == 0) {
         for (int g = 0; g < kGroups; ++g) mbar_init(smem_u32(&S.d_ready[g]), 1);
+        for (int sl = 0; sl < kSlots; ++sl) {
+            mbar_init(smem_u32(&S.full[sl]), kProducerWarps);      // one arrival per producer warp
+            mbar_init(smem_u32(&S.empty[sl]), 4);                  // one arrival per warp of the consuming group
+        }
         mbar_init(smem_u32(&S.w_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t f16_bytes = hdr->f16_bytes;
@@ -456,140 +540,199 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
 
     const long long n_tiles = (P.n + kTile - 1) / kTile;
-    // tile list of this CTA: blockIdx.x, +gridDim.x, ...; group g takes every kGroups-th entry
+    // tile list of this CTA: blockIdx.x, +gridDim.x, ...; entry k goes to group k % kGroups through slot k % kSlots
     const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    const int g = warp >> 2, q = warp & 3;
-    const uint32_t tg_mma = tmem_base + g * kColsPerGroup;                   // lane field 0: MMA operand addresses
-    const uint32_t tg = tg_mma + ((uint32_t)(q * 32) << 16);                 // this warp's 32-lane window
-    const uint32_t bar_d = smem_u32(&S.d_ready[g]);
-    const uint32_t w_base = smem_u32(S.w16);
-    uint32_t pd = 0;
-    const float inv_t = (float)(1.0 / (double)P.T);
-    const float step = (MODE == kModePdf) ? -inv_t : inv_t;
-    if (q == 0) mbar_wait(smem_u32(&S.w_bar), 0);                           // weights have landed in smem
+    if (warp >= kGroups * 4) {
+        // =========================== producer ==========================================================
+        const int row = (warp - kGroups * 4) * 32 + lane;
+        RawIn cur, nxt;
+        cur.wa = cur.wb = cur.wc = cur.oa = cur.ob = cur.oc = cur.r0 = cur.r1 = 0.0f;
+        nxt = cur;
+        auto index_of = [&](long long k, bool& valid) {
+            const long long i_raw = (blockIdx.x + k * gridDim.x) * kTile + row;
+            valid = i_raw < P.n;
+            return valid ? i_raw : (P.n - 1);               // tail rows recompute the last query, never store
+        };
+        bool valid = false, valid_n = false;
+        long long i = 0, i_n = 0;
+        if (my_tiles > 0) { i = index_of(0, valid); raw_load<MODE>(P, i, cur); }
+#pragma unroll 1
+        for (long long k = 0; k < my_tiles; ++k) {
+            if (k + 1 < my_tiles) { i_n = index_of(k + 1, valid_n); raw_load<MODE>(P, i_n, nxt); }
+            const int sl = (int)(k % kSlots);
+            const uint32_t use = (uint32_t)(k / kSlots);
 
-    for (long long k = g; k < my_tiles; k += kGroups) {
-        const long long tile = blockIdx.x + k * gridDim.x;
-        const long long i_raw = tile * kTile + q * 32 + lane;
-        const bool valid = i_raw < P.n;
-        const long long i = valid ? i_raw : (P.n - 1);      // tail rows recompute the last query, never store
-
-        float w0, w1, wiz;
-        load_wi(P, i, w0, w1, wiz);
-        float bp[4] = {0.f, 0.f, 0.f, 0.f};
-        {
+            // conditioning in domain coordinates (brdf_measured_disk.py:66-67, brdf_measured_spherical.py:76-77)
+            float w0, w1, wiz = cur.wc;
+            if (P.epilogue == kEpiRaw || P.epilogue == kEpiDisk) { w0 = cur.wa; w1 = cur.wb; }
+            else cart_to_spher(cur.wa, cur.wb, cur.wc, w0, w1);
             float e[kPE5];
             pe5_fast(w0, w1, e);
-            uint32_t c[12];
+            uint32_t c[11];
 #pragma unroll
             for (int j = 0; j < 11; ++j) c[j] = pack_h2(e[2 * j], e[2 * j + 1]);
-            c[11] = 0u;
-            tmem_st8(tg + kColA1 + 4, c);
-            tmem_st4(tg + kColA1 + 12, c[8], c[9], c[10], c[11]);
-            if (P.base) base_eval_smem(S, e, bp);           // PE3 is a prefix of PE5
-        }
-
-        float x0, x1, R = 1.0f, p0 = 1.0f;
-        float wox = 0.0f, woy = 0.0f, woz = 1.0f, theta_o = 0.0f;
-        if (MODE == kModePdf) {
-            load_wo(P, i, x0, x1, wox, woy, woz);
-            theta_o = x0;
-        } else {
-            if (P.x0) {
-                const float2 t = reinterpret_cast<const float2*>(P.x0)[i];
-                x0 = t.x; x1 = t.y;
+            float bp[4] = {0.f, 0.f, 0.f, 0.f};
+            if (P.base) base_eval_smem(S, e, bp);               // PE3 is a prefix of PE5
+            float x0, x1, p0 = 1.0f;
+            if (MODE == kModePdf) {
+                if (P.epilogue == kEpiRaw || P.epilogue == kEpiDisk) { x0 = cur.oa; x1 = cur.ob; }   // brdf_measured_disk.py:118-120
+                else cart_to_spher(cur.oa, cur.ob, cur.oc, x0, x1);                                  // brdf_measured_spherical.py:131-133
             } else {
-                base_draw_fast<DOMAIN>(bp, P.seed, P.offset, P.first_index + i, x0, x1);
+                if (P.x0) { x0 = cur.r0; x1 = cur.r1; }
+                else base_draw_fast<DOMAIN>(bp, P.seed, P.offset, P.first_index + i, x0, x1);
+                if (P.out_x0 && valid) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
+                if (MODE == kModeSample) p0 = __expf(base_logprob_fast<DOMAIN>(bp, x0, x1));
             }
-            if (P.out_x0 && valid) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
-            if (MODE == kModeSample) p0 = __expf(base_logprob_fast<DOMAIN>(bp, x0, x1));
+
+            mbar_wait<2000>(smem_u32(&S.empty[sl]), (use & 1u) ^ 1u);   // the group that used this slot last has read it
+            float (*f)[kTile] = S.slot[sl];
+#pragma unroll
+            for (int j = 0; j < 11; ++j) f[kFPe + j][row] = __uint_as_float(c[j]);
+            f[kFX][row] = x0; f[kFX + 1][row] = x1;
+            if (MODE == kModeSample) f[kFP0][row] = p0;
+            if (MODE == kModePdf) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) f[kFBp + j][row] = bp[j];
+                f[kFWiz][row] = wiz;
+                f[kFWo][row] = cur.oa; f[kFWo + 1][row] = cur.ob; f[kFWo + 2][row] = cur.oc;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&S.full[sl]));      // release: the stores above are visible to the waiters
+            cur = nxt; i = i_n; valid = valid_n;
         }
+    } else {
+        // =========================== workers ===========================================================
+        const int g = warp >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t tg_mma = tmem_base + g * kColsPerGroup;                   // lane field 0: MMA operand addresses
+        const uint32_t tg = tg_mma + ((uint32_t)(q * 32) << 16);                 // this warp's 32-lane window
+        const uint32_t bar_d = smem_u32(&S.d_ready[g]);
+        const uint32_t w_base = smem_u32(S.w16);
+        uint32_t pd = 0;
+        const float inv_t = (float)(1.0 / (double)P.T);
+        const float step = (MODE == kModePdf) ? -inv_t : inv_t;
+        if (q == 0) mbar_wait(smem_u32(&S.w_bar), 0);                           // weights have landed in smem
 
 #pragma unroll 1
-        for (int t = 0; t < P.T; ++t) {
-            const float tf = (float)t / (float)P.T;
-            const float alpha = (MODE == kModePdf) ? 1.0f - tf : tf;
-            // ---- state -> A1 columns 0..3 (hi parts, then lo parts); tangent seeds -> A_u, A_v chunk 0 ----
+        for (long long k = g; k < my_tiles; k += kGroups) {
+            const long long i_raw = (blockIdx.x + k * gridDim.x) * kTile + row;
+            const bool valid = i_raw < P.n;
+            const long long i = valid ? i_raw : (P.n - 1);
+            const int sl = (int)(k % kSlots);
+            const uint32_t use = (uint32_t)(k / kSlots);
+
+            // ---- take this row's record from the producer ----
+            float x0, x1, R = 1.0f, p0 = 1.0f;
+            mbar_wait(smem_u32(&S.full[sl]), use & 1u);
             {
-                float s0, s1, s2v, s3;
-                if (DOMAIN == kDisk) { s0 = x0; s1 = x1; s2v = alpha; s3 = 0.0f; }
-                else { __sincosf(x1, &s1, &s2v); s0 = x0; s3 = alpha; }
-                const uint32_t c01 = pack_h2(s0, s1), c23 = pack_h2(s2v, s3);
-                const uint32_t l01 = pack_h2(s0 - h2_lo(c01), s1 - h2_hi(c01));
-                const uint32_t l23 = pack_h2(s2v - h2_lo(c23), s3 - h2_hi(c23));
-                if (DOMAIN == kDisk) {
-                    // k: x0_hi x1_hi | a_hi a_lo | x0_lo x1_lo | 0 0
-                    tmem_st4(tg + kColA1, c01, (c23 & 0xffffu) | (l23 << 16), l01, 0u);
-                    if (TANGENTS) {
-                        const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx0: k = 0
-                        const uint32_t ev[8] = {0x3C000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx1: k = 1
-                        tmem_st8(tg + kColA + 16, eu);
-                        tmem_st8(tg + kColA + 32, ev);
-                    }
-                } else {
-                    // k: th_hi sin_hi | cos_hi a_hi | th_lo sin_lo | cos_lo a_lo
-                    tmem_st4(tg + kColA1, c01, c23, l01, l23);
-                    if (TANGENTS) {
-                        // d/dtheta: k = 0.  d/dphi: d(sin) = cos on k = 1, d(cos) = -sin on k = 2 (hi parts), lo parts
-                        // on k = 5, 6 (the weight image repeats W1[:,1], W1[:,2] there)
-                        const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                        const uint32_t ev[8] = {c23 << 16, (c01 >> 16) ^ 0x8000u, l23 << 16, (l01 >> 16) ^ 0x8000u,
-                                                0u, 0u, 0u, 0u};
-                        tmem_st8(tg + kColA + 16, eu);
-                        tmem_st8(tg + kColA + 32, ev);
+                const float (*f)[kTile] = S.slot[sl];
+                uint32_t c[12];
+#pragma unroll
+                for (int j = 0; j < 11; ++j) c[j] = __float_as_uint(f[kFPe + j][row]);
+                c[11] = 0u;
+                tmem_st8(tg + kColA1 + 4, c);
+                tmem_st4(tg + kColA1 + 12, c[8], c[9], c[10], c[11]);
+                x0 = f[kFX][row]; x1 = f[kFX + 1][row];
+                if (MODE == kModeSample) p0 = f[kFP0][row];
+            }
+            const float theta_o = x0;
+            if (MODE != kModePdf) {          // pdf mode reads the rest of the record at the end of the tile
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
+            }
+
+#pragma unroll 1
+            for (int t = 0; t < P.T; ++t) {
+                const float tf = (float)t / (float)P.T;
+                const float alpha = (MODE == kModePdf) ? 1.0f - tf : tf;
+                // ---- state -> A1 columns 0..3 (hi parts, then lo parts); tangent seeds -> A_u, A_v chunk 0 ----
+                {
+                    float s0, s1, s2v, s3;
+                    if (DOMAIN == kDisk) { s0 = x0; s1 = x1; s2v = alpha; s3 = 0.0f; }
+                    else { __sincosf(x1, &s1, &s2v); s0 = x0; s3 = alpha; }
+                    const uint32_t c01 = pack_h2(s0, s1), c23 = pack_h2(s2v, s3);
+                    const uint32_t l01 = pack_h2(s0 - h2_lo(c01), s1 - h2_hi(c01));
+                    const uint32_t l23 = pack_h2(s2v - h2_lo(c23), s3 - h2_hi(c23));
+                    if (DOMAIN == kDisk) {
+                        // k: x0_hi x1_hi | a_hi a_lo | x0_lo x1_lo | 0 0
+                        tmem_st4(tg + kColA1, c01, (c23 & 0xffffu) | (l23 << 16), l01, 0u);
+                        if (TANGENTS) {
+                            const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx0: k = 0
+                            const uint32_t ev[8] = {0x3C000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx1: k = 1
+                            tmem_st8(tg + kColA + 16, eu);
+                            tmem_st8(tg + kColA + 32, ev);
+                        }
+                    } else {
+                        // k: th_hi sin_hi | cos_hi a_hi | th_lo sin_lo | cos_lo a_lo
+                        tmem_st4(tg + kColA1, c01, c23, l01, l23);
+                        if (TANGENTS) {
+                            // d/dtheta: k = 0.  d/dphi: d(sin) = cos on k = 1, d(cos) = -sin on k = 2 (hi parts), lo
+                            // parts on k = 5, 6 (the weight image repeats W1[:,1], W1[:,2] there)
+                            const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                            const uint32_t ev[8] = {c23 << 16, (c01 >> 16) ^ 0x8000u, l23 << 16, (l01 >> 16) ^ 0x8000u,
+                                                    0u, 0u, 0u, 0u};
+                            tmem_st8(tg + kColA + 16, eu);
+                            tmem_st8(tg + kColA + 32, ev);
+                        }
                     }
                 }
-            }
-            publish_and_issue<TANGENTS>(g, q, 0, NH, tg_mma, w_base, bar_d);
+                publish_and_issue<TANGENTS>(g, q, 0, NH, tg_mma, w_base, bar_d);
 
-            // ---- activation rounds: layer 1 and the hidden layers share one instruction stream ----
+                // ---- activation rounds: layer 1 and the hidden layers share one instruction stream ----
 #pragma unroll 1
-            for (int l = 0; l < NH; ++l) {
+                for (int l = 0; l < NH; ++l) {
+                    mbar_wait(bar_d, pd); pd ^= 1u;
+                    tc_fence_after();
+                    float za[16], ua[TANGENTS ? 16 : 1], va[TANGENTS ? 16 : 1];
+                    float zb[16], ub[TANGENTS ? 16 : 1], vb[TANGENTS ? 16 : 1];
+                    tmem_ld16(tg + kColD, za);
+                    if (TANGENTS) { tmem_ld16(tg + kColD + 32, ua); tmem_ld16(tg + kColD + 64, va); }
+                    tc_wait_ld();
+                    tmem_ld16(tg + kColD + 16, zb);            // second half streams in under the first half's math
+                    if (TANGENTS) { tmem_ld16(tg + kColD + 32 + 16, ub); tmem_ld16(tg + kColD + 64 + 16, vb); }
+                    uint32_t ph[8], pu[8], pv[8];
+                    activate16<TANGENTS, ACT>(za, ua, va, ph, pu, pv);
+                    tmem_st8(tg + kColA, ph);
+                    if (TANGENTS) { tmem_st8(tg + kColA + 16, pu); tmem_st8(tg + kColA + 32, pv); }
+                    tc_wait_ld();
+                    activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
+                    tmem_st8(tg + kColA + 8, ph);
+                    if (TANGENTS) { tmem_st8(tg + kColA + 16 + 8, pu); tmem_st8(tg + kColA + 32 + 8, pv); }
+                    publish_and_issue<TANGENTS>(g, q, l + 1, NH, tg_mma, w_base, bar_d);
+                }
+
+                // ---- output round: d, dd/dx0, dd/dx1 ----
                 mbar_wait(bar_d, pd); pd ^= 1u;
                 tc_fence_after();
-                float za[16], ua[TANGENTS ? 16 : 1], va[TANGENTS ? 16 : 1];
-                float zb[16], ub[TANGENTS ? 16 : 1], vb[TANGENTS ? 16 : 1];
-                tmem_ld16(tg + kColD, za);
-                if (TANGENTS) { tmem_ld16(tg + kColD + 32, ua); tmem_ld16(tg + kColD + 64, va); }
+                float d0, d1, du0 = 0.f, du1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+                tmem_ld2(tg + kColD, d0, d1);
+                if (TANGENTS) { tmem_ld2(tg + kColD + 32, du0, du1); tmem_ld2(tg + kColD + 64, dv0, dv1); }
                 tc_wait_ld();
-                tmem_ld16(tg + kColD + 16, zb);            // second half streams in under the first half's math
-                if (TANGENTS) { tmem_ld16(tg + kColD + 32 + 16, ub); tmem_ld16(tg + kColD + 64 + 16, vb); }
-                uint32_t ph[8], pu[8], pv[8];
-                activate16<TANGENTS, ACT>(za, ua, va, ph, pu, pv);
-                tmem_st8(tg + kColA, ph);
-                if (TANGENTS) { tmem_st8(tg + kColA + 16, pu); tmem_st8(tg + kColA + 32, pv); }
-                tc_wait_ld();
-                activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
-                tmem_st8(tg + kColA + 8, ph);
-                if (TANGENTS) { tmem_st8(tg + kColA + 16 + 8, pu); tmem_st8(tg + kColA + 32 + 8, pv); }
-                publish_and_issue<TANGENTS>(g, q, l + 1, NH, tg_mma, w_base, bar_d);
+                if (TANGENTS) {
+                    const float j00 = fmaf(step, du0, 1.0f), j01 = step * dv0;
+                    const float j10 = step * du1, j11 = fmaf(step, dv1, 1.0f);
+                    const float det = j00 * j11 - j01 * j10;
+                    R = (MODE == kModePdf) ? R * det : __fdividef(R, det);
+                }
+                x0 = fmaf(step, d0, x0);
+                x1 = fmaf(step, d1, x1);
             }
 
-            // ---- output round: d, dd/dx0, dd/dx1 ----
-            mbar_wait(bar_d, pd); pd ^= 1u;
-            tc_fence_after();
-            float d0, d1, du0 = 0.f, du1 = 0.f, dv0 = 0.f, dv1 = 0.f;
-            tmem_ld2(tg + kColD, d0, d1);
-            if (TANGENTS) { tmem_ld2(tg + kColD + 32, du0, du1); tmem_ld2(tg + kColD + 64, dv0, dv1); }
-            tc_wait_ld();
-            if (TANGENTS) {
-                const float j00 = fmaf(step, du0, 1.0f), j01 = step * dv0;
-                const float j10 = step * du1, j11 = fmaf(step, dv1, 1.0f);
-                const float det = j00 * j11 - j01 * j10;
-                R = (MODE == kModePdf) ? R * det : __fdividef(R, det);
-            }
-            x0 = fmaf(step, d0, x0);
-            x1 = fmaf(step, d1, x1);
-        }
-
-        if (valid) {
             if (MODE == kModeSample) {
-                store_sample<true>(P, i, x0, x1, p0 * R);
+                if (valid) store_sample<true>(P, i, x0, x1, p0 * R);
             } else if (MODE == kModePdf) {
-                store_pdf<true>(P, i, __expf(base_logprob_fast<DOMAIN>(bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
+                const float (*f)[kTile] = S.slot[sl];
+                float bp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bp[j] = f[kFBp + j][row];
+                const float wiz = f[kFWiz][row], wox = f[kFWo][row], woy = f[kFWo + 1][row], woz = f[kFWo + 2][row];
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
+                if (valid)
+                    store_pdf<true>(P, i, __expf(base_logprob_fast<DOMAIN>(bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
             } else {
-                reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
+                if (valid) reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
             }
         }
     }
@@ -613,7 +756,13 @@ static int launch_tc_t(const FlowParams& P, cudaStream_t stream) {
     long long grid = sms;
     if (grid > tiles) grid = tiles;
     if (grid < 1) return 0;
-    flow_tc_kernel<DOMAIN, MODE, ACT><<<(unsigned)grid, kTcThreads, 0, stream>>>(P);
+    static bool attr_set = false;            // per instantiation; benign if two host threads race (same value)
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(flow_tc_kernel<DOMAIN, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(TcSmem)) != cudaSuccess) return -3;
+        attr_set = true;
+    }
+    flow_tc_kernel<DOMAIN, MODE, ACT><<<(unsigned)grid, kTcThreads, sizeof(TcSmem), stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 

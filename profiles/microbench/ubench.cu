@@ -286,6 +286,32 @@ __device__ __forceinline__ long long form_probe(int lane, uint32_t& sink) {
     return t1 - t0;
 }
 
+// MUFU / FP32 overlap at realistic ratios: NT independent tanh.f32 chains and NS independent scalar FFMA chains
+template <int NT, int NS>
+__device__ __forceinline__ long long overlap_probe(int lane, uint32_t& sink) {
+    float x[NT > 0 ? NT : 1], y[NS > 0 ? NS : 1];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) x[i] = 0.01f * (lane + i);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) y[i] = 1.0f + 0.001f * (lane + i);
+    const float m = 0.999f;
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 256; ++it) {
+#pragma unroll
+        for (int i = 0; i < (NT > NS ? NT : NS); ++i) {
+            if (i < NT) asm volatile("tanh.approx.f32 %0, %0;" : "+f"(x[i]));
+            if (i < NS) asm volatile("fma.rn.f32 %0, %0, %1, %1;" : "+f"(y[i]) : "f"(m));
+        }
+    }
+    const long long t1 = clock64();
+#pragma unroll
+    for (int i = 0; i < NT; ++i) sink += __float_as_uint(x[i]);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) sink += __float_as_uint(y[i]);
+    return t1 - t0;
+}
+
 struct Res { long long cyc[16]; };
 
 // test ids
@@ -562,7 +588,13 @@ __global__ void __launch_bounds__(512, 1) ubench(int test, int nwarps, int kpara
             case 18: t1 = form_probe<1>(lane, sink); break;
             case 19: t1 = form_probe<2>(lane, sink); break;
             case 20: t1 = form_probe<3>(lane, sink); break;
-            default: t1 = form_probe<4>(lane, sink); break;
+            case 21: t1 = form_probe<4>(lane, sink); break;
+            case 22: t1 = overlap_probe<8, 0>(lane, sink); break;
+            case 23: t1 = overlap_probe<0, 48>(lane, sink); break;
+            case 24: t1 = overlap_probe<8, 16>(lane, sink); break;
+            case 25: t1 = overlap_probe<8, 32>(lane, sink); break;
+            case 26: t1 = overlap_probe<8, 48>(lane, sink); break;
+            default: t1 = overlap_probe<8, 64>(lane, sink); break;
         }
     }
     if (lane == 0 && warp < 16 && test != T_MMA) out[blockIdx.x].cyc[warp] = (t1 - t0);
@@ -675,10 +707,10 @@ int main() {
         for (int w : {1, 4, 8, 12, 16}) run("cvt.f16x2", T_PACK, w, 0, grid, 16 * 32.0, "cvt-instr-lanes");
         for (int w : {4, 8, 12, 16}) run("act-mix", T_MIX, w, 0, grid, 16 * 32.0, "activations");
         {
-            const char* names[22] = {"tanh x8", "cvt x8", "fma2 x8", "hfma2 x8", "prmt x8", "tanh8+cvt8", "tanh8+fma2_8", "cvt8+fma2_8",
+            const char* names[28] = {"tanh x8", "cvt x8", "fma2 x8", "hfma2 x8", "prmt x8", "tanh8+cvt8", "tanh8+fma2_8", "cvt8+fma2_8",
                                      "tanh8+hfma2_8", "cvt8+hfma2_8", "fma2_8+hfma2_8", "tanh8+cvt8+fma2_8", "tanh4+cvt6+fma2_8",
-                                     "cvt8+prmt8", "tanh8+prmt8", "act-math f32x2 (16 act)", "act-math half2 (16 act)", "form0 f32x2", "form1 scalar f32", "form2 half2 tail", "form3 half2 tangent product", "form4 all half2"};
-            for (int c = 15; c < 22; ++c) for (int w : {4, 8, 12, 16}) run(names[c], T_TANH_PACK, w, c, grid, 1.0, "(per-thread inner iterations x warps)/clk");
+                                     "cvt8+prmt8", "tanh8+prmt8", "act-math f32x2 (16 act)", "act-math half2 (16 act)", "form0 f32x2", "form1 scalar f32", "form2 half2 tail", "form3 half2 tangent product", "form4 all half2", "ovl tanh8", "ovl ffma48", "ovl tanh8+ffma16", "ovl tanh8+ffma32", "ovl tanh8+ffma48", "ovl tanh8+ffma64"};
+            for (int c = 22; c < 28; ++c) for (int w : {4, 12, 16}) run(names[c], T_TANH_PACK, w, c, grid, 1.0, "(per-thread inner iterations x warps)/clk");
         }
         for (int k : {1, 2, 3, 6, 8, 12}) run("mma", T_MMA, 1, k, grid, 0, "");
         for (int w : {4, 8, 12}) for (int k : {6, 8}) run("chain", T_CHAIN, w, k, grid, 1.0, "rounds");
