@@ -272,13 +272,19 @@ def main():
     peak, peak_src = measured_peak()
     per_gpu_qps = n * args.steps / (ms * 1e-3)
     achieved = per_gpu_qps * F / 1e12
+    # DRAM traffic of ONE launch from the committed ncu --set full capture of this exact configuration
+    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1h_ncu_tc16_disk_summary.txt); other configs: null
+    traffic = 424.68e6 if (args.workload == "disk" and n == 4096 * 4096 and args.precision == "tc16") else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": "profiles/r1h_ncu_tc16_disk_summary.txt (bytes per launch)"
+                if traffic else None, "peak_source": peak_src,
                 "kernel": "flow_tc_kernel" if args.precision == "tc16" else "flow_simt_kernel",
                 "flops_per_query": F, "avg_launch_ms": ms / args.steps,
                 "hbm_algorithmic_bytes_per_query": 28, "hbm_achieved_gbs": per_gpu_qps * 28 / 1e9,
+                "mufu_ceiling_frac": 0.43 if args.workload == "disk" else 0.46,
                 "note": "algorithmic FLOPs (unpadded layer shapes, value + 2 tangent columns) x queries per launch "
-                        "/ CUDA-event time per launch; per GPU"}
+                        "/ CUDA-event time per launch; per GPU. mufu_ceiling_frac = the fraction of the tensor roofline at "
+                        "which the 16 tanh/clk/SM MUFU rate saturates (one tanh per activation; DESIGN.md 4.1)"}
     line = {"metric": "BSDF samples/sec (sample+pdf)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,

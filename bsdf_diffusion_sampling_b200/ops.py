@@ -96,6 +96,22 @@ def _(wi, flow_blob, base, x0, precision, domain, epilogue, T, hidden, n_hidden,
             wi.new_empty((n if want_x0 else 0, 2)))
 
 
+@torch.library.custom_op("bsdfdiff::sample_out", mutates_args=("out_dir", "out_pdf"), device_types="cuda")
+def _sample_out_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor, x0: Optional[torch.Tensor],
+                   out_dir: torch.Tensor, out_pdf: torch.Tensor,
+                   precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
+                   seed: int, offset: int, first_index: int) -> None:
+    """As ``bsdfdiff::sample`` but writes into caller-owned buffers (no allocation: streaming pipelines)."""
+    n = wi.shape[0]
+    with torch.cuda.device(wi.device):
+        rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
+                                      flow_blob.data_ptr() if flow_blob is not None else None,
+                                      hidden, n_hidden, base.data_ptr(), x0.data_ptr() if x0 is not None else None,
+                                      seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(), None,
+                                      _stream(wi))
+    _lib.check(rc, "bsdfdiff_sample")
+
+
 @torch.library.custom_op("bsdfdiff::pdf", mutates_args=(), device_types="cuda")
 def _pdf_op(wo: torch.Tensor, wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor,
             precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int) -> torch.Tensor:
@@ -181,6 +197,27 @@ def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int 
         seed, offset = next_philox(wi.device)
     return _sample_op(wi, flow.blob, base, x0, _resolve_precision(precision), flow.domain, epilogue, int(T),
                       flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), bool(return_x0))
+
+
+def sample_into(wi: torch.Tensor, flow, base: torch.Tensor, T: int, out_dir: torch.Tensor, out_pdf: torch.Tensor, *,
+                epilogue: int = EPI_RAW, x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0,
+                first_index: int = 0, precision=None) -> None:
+    """``sample`` into caller-owned contiguous fp32 CUDA buffers ``out_dir`` [n,2|3] and ``out_pdf`` [n]."""
+    _require_cuda(wi, "sample_into")
+    wi = _f32c(wi)
+    n, cols = wi.shape[0], (2 if epilogue == EPI_RAW else 3)
+    for t, shape in ((out_dir, (n, cols)), (out_pdf, (n,))):
+        if (not t.is_cuda) or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise ValueError(f"bsdfdiff.sample_into: output must be a contiguous fp32 CUDA tensor of shape {shape}")
+    if T < 0 or (T == 0) != (flow.blob is None):
+        raise ValueError("T must be >= 1 (T == 0 only with NullFlow: base distribution alone)")
+    if x0 is not None:
+        x0 = _f32c(x0, wi.device)
+        seed, offset = 0, 0
+    elif seed is None:
+        seed, offset = next_philox(wi.device)
+    _sample_out_op(wi, flow.blob, base, x0, out_dir, out_pdf, _resolve_precision(precision), flow.domain, epilogue,
+                   int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index))
 
 
 def pdf(wo: torch.Tensor, wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,

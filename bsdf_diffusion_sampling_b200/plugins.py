@@ -94,46 +94,55 @@ class NeuralBSDFSampler:
 
     # -- host-buffer entry point (what a renderer that keeps its wavefront on the host calls) ---------
     def sample_host(self, wi_host: torch.Tensor, wo_host: torch.Tensor, pdf_host: torch.Tensor, *, seed: int,
-                    offset: int = 0, first_index: int = 0, chunk: int = 1 << 21, device=None) -> int:
+                    offset: int = 0, first_index: int = 0, chunk: int = 1 << 20, device=None) -> int:
         """Sample for ``wi_host`` [N,3] (pinned CPU memory), writing ``wo_host`` [N,3] / ``pdf_host`` [N]
         (pinned).  The batch is streamed in chunks over three CUDA streams so the H2D copy of chunk k+1,
-        the kernel of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full duplex).  Philox
-        counters are global row indices, so the result equals one whole-batch launch.  Returns the
-        number of kernel launches."""
+        the kernel of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full duplex).  All device
+        buffers (3 input + 3 output slots) are allocated once and reused -- nothing is allocated or freed
+        while the pipeline runs.  Philox counters are global row indices, so the result equals one
+        whole-batch launch.  Returns the number of kernel launches."""
         device = torch.device(device or self.base.device)
         n = wi_host.shape[0]
-        if not hasattr(self, "_host_pipe") or self._host_pipe[0] < chunk or self._host_pipe[1] != device:
-            bufs = [(torch.empty((chunk, 3), dtype=torch.float32, device=device),) for _ in range(3)]
-            self._host_pipe = (chunk, device, bufs, [torch.cuda.Stream(device) for _ in range(3)])
-        _, _, bufs, (s_in, s_k, s_out) = self._host_pipe
+        pipe = getattr(self, "_host_pipe", None)
+        if pipe is None or pipe[0] != chunk or pipe[1] != device:
+            bufs = [(torch.empty((chunk, 3), dtype=torch.float32, device=device),
+                     torch.empty((chunk, 3), dtype=torch.float32, device=device),
+                     torch.empty((chunk,), dtype=torch.float32, device=device)) for _ in range(3)]
+            pipe = self._host_pipe = (chunk, device, bufs, [torch.cuda.Stream(device) for _ in range(3)])
+        _, _, bufs, (s_in, s_k, s_out) = pipe
         cur = torch.cuda.current_stream(device)
         for s in (s_in, s_k, s_out):
             s.wait_stream(cur)
         launches = 0
-        pending = []            # (event_kernel_done, wo_dev, pdf_dev, a, b)
-        free_ev = [None, None, None]
+        in_free = [None, None, None]         # kernel that last read input slot j has finished
+        out_free = [None, None, None]        # D2H copies that last read output slot j have finished
         for k, a in enumerate(range(0, n, chunk)):
-            b = min(n, a + chunk)
-            (wi_dev,) = bufs[k % 3]
+            b, j = min(n, a + chunk), k % 3
+            wi_dev, wo_dev, pdf_dev = bufs[j]
             with torch.cuda.stream(s_in):
-                if free_ev[k % 3] is not None:
-                    s_in.wait_event(free_ev[k % 3])                 # kernel that last read this buffer is done
+                if in_free[j] is not None:
+                    s_in.wait_event(in_free[j])
                 wi_dev[: b - a].copy_(wi_host[a:b], non_blocking=True)
                 ev_in = torch.cuda.Event()
                 ev_in.record(s_in)
             with torch.cuda.stream(s_k):
                 s_k.wait_event(ev_in)
-                wo_dev, pdf_dev = self.sample(wi_dev[: b - a], seed=seed, offset=offset, first_index=first_index + a)
+                if out_free[j] is not None:
+                    s_k.wait_event(out_free[j])
+                ops.sample_into(wi_dev[: b - a], self.flow, self.base, self.T, wo_dev[: b - a], pdf_dev[: b - a],
+                                epilogue=self.epilogue, seed=seed, offset=offset, first_index=first_index + a,
+                                precision=self.precision)
                 launches += 1
                 ev_k = torch.cuda.Event()
                 ev_k.record(s_k)
-                free_ev[k % 3] = ev_k
+                in_free[j] = ev_k
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_k)
-                wo_host[a:b].copy_(wo_dev, non_blocking=True)
-                pdf_host[a:b].copy_(pdf_dev, non_blocking=True)
-                wo_dev.record_stream(s_out)
-                pdf_dev.record_stream(s_out)
+                wo_host[a:b].copy_(wo_dev[: b - a], non_blocking=True)
+                pdf_host[a:b].copy_(pdf_dev[: b - a], non_blocking=True)
+                ev_o = torch.cuda.Event()
+                ev_o.record(s_out)
+                out_free[j] = ev_o
         cur.wait_stream(s_out)
         cur.wait_stream(s_k)
         return launches
