@@ -3,7 +3,7 @@
 // One persistent CTA per SM, kGroups worker groups of 128 threads (4 warps; thread <-> TMEM lane <->
 // query row).  Each group owns one 128-query tile at a time and runs the WHOLE T-step flow for it on
 // chip; the groups are independent pipelines that overlap each other's tensor-core round trips
-// (TMEM holds exactly three tiles: 3 x 160 of the 512 columns).
+// (TMEM holds exactly four tiles: 4 x 128 of the 512 columns).
 //
 //   per tile:  PE5(wi) -> fp16 -> TMEM A1[:,8:30];  base net, x0 (Philox or replay), p0   (fp32)
 //   per step:  state (hi/lo fp16 split) -> A1[:,0:8];  tangent seeds d(state)/dx -> A_u, A_v (K chunk 0)
@@ -33,30 +33,48 @@
 // the packed blob's fp16 image is ALREADY the UMMA canonical K-major layout, staged with one
 // cp.async.bulk (TMA).  Every weight matrix is stored as fp16 hi + fp16 lo; the value path multiplies
 // by both (weights effectively ~22 bits: weight rounding was the dominant fp16 error), the tangent path
-// by hi only.  Accumulators are fp32 in TMEM.  x, det, R, pdf stay fp32 in registers for all T steps.
+// by hi only.  Value accumulators (z) and the output round are fp32 in TMEM; the hidden-layer TANGENT
+// accumulators are fp16 (idesc D format f16) and are read back two per register with tcgen05.ld .pack::16b,
+// so s2 and the tangent products run as half2 instructions and need no conversion.  x, det, R, pdf stay
+// fp32 in registers for all T steps.
 //
 // tanh-form sigmoid: hidden-layer weights are pre-scaled by 1/2 (exact), so the MMA yields zh = z/2 and
 // duh = du/2:   t = tanh(zh);  silu(z) = zh + zh t;  2 silu'(z) = (1 + t) + silu(z) (1 - t);
-// u_out = 2 silu'(z) * duh  -> one MUFU op per activation and no rescaling.  The fp32 arithmetic is
-// issued as packed f32x2 instructions (two activations per issue slot).  MUFU.TANH (16 / clk / SM) is the
-// binding pipe of this kernel; the FMA pipe (f32x2 at half rate) and the ALU pipe (F2FP packs) overlap it.
+// u_out = 2 silu'(z) * duh  -> one MUFU op per activation and no rescaling.  Per neuron PAIR the math is
+// 2 MUFU.TANH + 1 fma.f32x2 (h) + 2 cvt.f16x2 (h, t) + 5 half2 ops (1-t, 1+t, s2, s2 du, s2 dv): measured
+// MUFU-bound in isolation (16 tanh / clk / SM; profiles/microbench "form2"), where the all-fp32 formulation
+// was dispatch-bound at 10.7.
 //
-// TMEM map (512 columns allocated; per group 160 columns at g*160):
-//   [  0, 96)  D_z | D_u | D_v   fp32 accumulators, 32 columns each (output round uses 16 of each)
-//   [ 96,144)  A_h | A_u | A_v   fp16 operands, K=32 -> 16 columns each
-//   [144,160)  A1                first-layer operand: cols 0..3 state (rewritten per step), 4..15 PE5(wi)
+// TMEM map (512 columns allocated; per group 128 columns at g*128):
+//   [  0, 32)  D_z         fp32 value accumulators (output round: 16 columns)
+//   [ 32, 64)  D_u         tangent accumulators: fp16 in the hidden rounds, fp32 (16 columns) in the output round
+//   [ 64, 96)  D_v         same; its first 16 columns are ALSO A_u (see below)
+//   [ 64, 80)  A_u         fp16 operand, K=32 -> 16 columns
+//   [ 96,112)  A_h / A1    fp16 operand of the hidden rounds; at every step start it is rewritten as the first-layer
+//                          operand A1 (cols 0..3 state, 4..15 PE5(wi) re-read from the tile's shared-memory record)
+//   [112,128)  A_v         fp16 operand
+// A_u and D_v overlap so that a tile needs 128 instead of 144 columns (four tiles in flight, not three).  A round
+// issues its MMAs in the order  u (reads A_u) ; z (four MMAs) ; v (writes D_v):  tcgen05.mma instructions of one
+// thread execute in issue order, so A_u has been consumed five MMAs before the first write to D_v; threads only
+// write A_u after their tcgen05.ld of D_v has completed (tcgen05.wait::ld).  BSDFDIFF_TC_NOALIAS builds the
+// non-overlapping 144-column map (three groups) that the aliased build is checked against bit for bit.
 #include "common.cuh"
 
 namespace bsdfdiff {
 
 #ifndef BSDFDIFF_TC_GROUPS
-#define BSDFDIFF_TC_GROUPS 3      // tuning builds only: 1 or 2 groups isolate the per-round latency chain
+#ifdef BSDFDIFF_TC_NOALIAS
+#define BSDFDIFF_TC_GROUPS 3      // the 144-column map: only three tiles fit
+#else
+#define BSDFDIFF_TC_GROUPS 4      // tuning builds only: 1 or 2 groups isolate the per-round latency chain
+#endif
 #endif
 constexpr int kGroups = BSDFDIFF_TC_GROUPS;
 constexpr int kWorkerThreads = kGroups * 128;
 constexpr int kProducerWarps = 4;                  // one 128-thread producer group: thread <-> query row of a tile
 constexpr int kTcThreads = kWorkerThreads + 32 * kProducerWarps;
-constexpr int kSlots = kGroups + 1;                // prologue ring: the producer runs one tile ahead of the groups
+constexpr int kSlots = kGroups + 2;                // prologue ring: every group holds its slot for the whole tile (PE5 is
+                                                   // re-read each step), the producer runs up to two tiles ahead
 // per-query record handed from the producer to the worker thread of the same row (field-major in shared memory,
 // slot[field][row], so both sides access consecutive words)
 constexpr int kFPe = 0;                            // 11 words: PE5(wi) as packed fp16 pairs (A1 columns 4..14)
@@ -67,9 +85,16 @@ constexpr int kFWiz = 18;                          // wi_z, wo (pdf-mode masks)
 constexpr int kFWo = 19;
 constexpr int kFields = 22;
 constexpr int kTile = 128;
-constexpr int kColsPerGroup = 160;
-constexpr int kColD = 0, kColA = 96, kColA1 = 144;
+#ifdef BSDFDIFF_TC_NOALIAS
+constexpr int kColsPerGroup = 144;
+constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 96, kColAh = 112, kColAv = 128;
+#else
+constexpr int kColsPerGroup = 128;
+constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 64, kColAh = 96, kColAv = 112;
+#endif
+constexpr int kColA1 = kColAh;
 constexpr int kTmemCols = 512;
+static_assert(kGroups * kColsPerGroup <= kTmemCols, "TMEM budget");
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -166,6 +191,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr) : "memory");
 }
+// 16 columns of fp16 accumulators (one half per 32-bit column) -> 8 registers, two neurons per register
+__device__ __forceinline__ void tmem_ld8_pack16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
     uint32_t x, y;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(taddr) : "memory");
@@ -217,53 +248,68 @@ __device__ __forceinline__ float tanh_approx(float x) {
     float t; asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x)); return t;
 }
 
+// packed fp16 pairs
+__device__ __forceinline__ uint32_t hadd2_(uint32_t a, uint32_t b) {
+    uint32_t d; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t hsub2_(uint32_t a, uint32_t b) {
+    uint32_t d; asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t hmul2_(uint32_t a, uint32_t b) {
+    uint32_t d; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t hfma2_(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 // shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
 __device__ __forceinline__ uint64_t make_b_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) |
            ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
-// instruction descriptor: D fp32, A/B fp16, both K-major, M=128 (cute::UMMA::InstrDescriptor)
-__host__ __device__ constexpr uint32_t make_idesc(int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// instruction descriptor: D fp32 or fp16, A/B fp16, both K-major, M=128 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t make_idesc(int N, bool d_f32) {
+    return (d_f32 ? (1u << 4) : 0u) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------------
-// activations on a pair of neurons.  Input zh = z/2 (packed pair).  Output h = silu(z), s2 = 2 silu'(z).
-//   ACT 0: fp32 exp form (cross-check variant), ACT 1: tanh.approx.f32 + f32x2 arithmetic
+// One activation pass over 16 neurons of this thread's row.  Inputs: zh = z/2 (fp32, from TMEM) and the packed
+// fp16 tangent pre-activations duh = du/2, dvh = dv/2.  Outputs are the next round's fp16 operand words:
+//   h = silu(z) = zh + zh t,   s2 = 2 silu'(z) = (1 + t) + h (1 - t),   u = s2 duh,   v = s2 dvh,   t = tanh(zh)
+//   ACT 1: tanh.approx.f32; h in fp32 (f32x2 fma), s2 and the products in half2
+//   ACT 0: fp32 exp form for h and s2 (cross-check variant), products in half2
 // ------------------------------------------------------------------------------------------------
-template <int ACT>
-__device__ __forceinline__ void silu_pair2(float zh0, float zh1, f32x2& h, f32x2& s2) {
-    if (ACT == 0) {
-        float hh[2], ss[2];
-        const float zz[2] = {2.0f * zh0, 2.0f * zh1};
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float s = __fdividef(1.0f, 1.0f + __expf(-zz[i]));
-            hh[i] = zz[i] * s;
-            ss[i] = 2.0f * s * fmaf(zz[i], 1.0f - s, 1.0f);
-        }
-        h = pk2(hh[0], hh[1]); s2 = pk2(ss[0], ss[1]);
-    } else {
-        const f32x2 one = pk2(1.0f, 1.0f);
-        const f32x2 zh = pk2(zh0, zh1);
-        const f32x2 t = pk2(tanh_approx(zh0), tanh_approx(zh1));
-        h = fma2(zh, t, zh);                       // zh (1 + t)
-        s2 = fma2(h, sub2(one, t), add2(one, t));  // (1 + t) + h (1 - t)
-    }
-}
-
-// One activation pass over 16 neurons of this thread's row: z, du, dv (fp32, from TMEM) -> fp16 operand words.
 template <bool TANGENTS, int ACT>
-__device__ __forceinline__ void activate16(const float* z, const float* du, const float* dv,
+__device__ __forceinline__ void activate16(const float* z, const uint32_t* du, const uint32_t* dv,
                                            uint32_t* ph, uint32_t* pu, uint32_t* pv) {
+    constexpr uint32_t kOneH2 = 0x3C003C00u;
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
-        f32x2 h, s2;
-        silu_pair2<ACT>(z[j], z[j + 1], h, s2);
-        ph[j >> 1] = pack_h2(h);
+        uint32_t h16, s16 = 0u;
+        if (ACT == 0) {
+            float hh[2], ss[2];
+            const float zz[2] = {2.0f * z[j], 2.0f * z[j + 1]};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const float s = __fdividef(1.0f, 1.0f + __expf(-zz[i]));
+                hh[i] = zz[i] * s;
+                ss[i] = 2.0f * s * fmaf(zz[i], 1.0f - s, 1.0f);
+            }
+            h16 = pack_h2(hh[0], hh[1]);
+            if (TANGENTS) s16 = pack_h2(ss[0], ss[1]);
+        } else {
+            const float t0 = tanh_approx(z[j]), t1 = tanh_approx(z[j + 1]);
+            const f32x2 zh = pk2(z[j], z[j + 1]);
+            h16 = pack_h2(fma2(zh, pk2(t0, t1), zh));                 // zh (1 + t)
+            if (TANGENTS) {
+                const uint32_t t16 = pack_h2(t0, t1);
+                s16 = hfma2_(h16, hsub2_(kOneH2, t16), hadd2_(kOneH2, t16));   // (1 + t) + h (1 - t)
+            }
+        }
+        ph[j >> 1] = h16;
         if (TANGENTS) {
-            pu[j >> 1] = pack_h2(mul2(s2, pk2(du[j], du[j + 1])));
-            pv[j >> 1] = pack_h2(mul2(s2, pk2(dv[j], dv[j + 1])));
+            pu[j >> 1] = hmul2_(s16, du[j >> 1]);
+            pv[j >> 1] = hmul2_(s16, dv[j >> 1]);
         }
     }
 }
@@ -404,37 +450,39 @@ __device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, 
 // Issue one round of MMAs for a group (executed by ONE thread; every operand is warp-uniform).  Each layer's
 // operand image = HI [N x 32] then LO [N x 32] (W = hi + lo): the value path accumulates A.hi^T + A.lo^T,
 // tangents use hi only.  type 0: first layer (tangent seeds are K=16 operands in A_u/A_v chunk 0),
-// 1..NH-1: hidden layer, NH: output layer (N = 16).
+// 1..NH-1: hidden layer, NH: output layer (N = 16, fp32 accumulators throughout).
+// Order: u, z, v -- A_u is read first and D_v (which overlaps A_u) is written last.
 template <bool TANGENTS>
 __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint32_t w_base, uint32_t bar) {
-    constexpr uint32_t idesc32 = make_idesc(32), idesc16 = make_idesc(16);
+    constexpr uint32_t idz = make_idesc(32, true), idt = make_idesc(32, false), ido = make_idesc(16, true);
     if (type < NH) {
         const uint64_t b = make_b_desc(w_base + 4096u * type, 512, 128);
-        const uint32_t a = tg + (type == 0 ? kColA1 : kColA);
-        mma_ts<0>(tg + kColD, a, b, idesc32);
-        mma_ts<1>(tg + kColD, a + 8, b + (1024 >> 4), idesc32);
-        mma_ts<1>(tg + kColD, a, b + (2048 >> 4), idesc32);
-        mma_ts<1>(tg + kColD, a + 8, b + (3072 >> 4), idesc32);
+        const uint32_t a = tg + (type == 0 ? kColA1 : kColAh);
         if (TANGENTS) {
-            mma_ts<0>(tg + kColD + 32, tg + kColA + 16, b, idesc32);
-            mma_ts<0>(tg + kColD + 64, tg + kColA + 32, b, idesc32);
-            if (type != 0) {
-                mma_ts<1>(tg + kColD + 32, tg + kColA + 16 + 8, b + (1024 >> 4), idesc32);
-                mma_ts<1>(tg + kColD + 64, tg + kColA + 32 + 8, b + (1024 >> 4), idesc32);
-            }
+            mma_ts<0>(tg + kColDu, tg + kColAu, b, idt);
+            if (type != 0) mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + (1024 >> 4), idt);
+        }
+        mma_ts<0>(tg + kColDz, a, b, idz);
+        mma_ts<1>(tg + kColDz, a + 8, b + (1024 >> 4), idz);
+        mma_ts<1>(tg + kColDz, a, b + (2048 >> 4), idz);
+        mma_ts<1>(tg + kColDz, a + 8, b + (3072 >> 4), idz);
+        if (TANGENTS) {
+            mma_ts<0>(tg + kColDv, tg + kColAv, b, idt);
+            if (type != 0) mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + (1024 >> 4), idt);
         }
     } else {                                        // output layer, N = 16
         const uint64_t b = make_b_desc(w_base + 4096u * NH, 256, 128);
-        mma_ts<0>(tg + kColD, tg + kColA, b, idesc16);
-        mma_ts<1>(tg + kColD, tg + kColA + 8, b + (512 >> 4), idesc16);
-        mma_ts<1>(tg + kColD, tg + kColA, b + (1024 >> 4), idesc16);
-        mma_ts<1>(tg + kColD, tg + kColA + 8, b + (1536 >> 4), idesc16);
         if (TANGENTS) {
-#pragma unroll
-            for (int c = 1; c < 3; ++c) {
-                mma_ts<0>(tg + kColD + 32 * c, tg + kColA + 16 * c, b, idesc16);
-                mma_ts<1>(tg + kColD + 32 * c, tg + kColA + 16 * c + 8, b + (512 >> 4), idesc16);
-            }
+            mma_ts<0>(tg + kColDu, tg + kColAu, b, ido);
+            mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + (512 >> 4), ido);
+        }
+        mma_ts<0>(tg + kColDz, tg + kColAh, b, ido);
+        mma_ts<1>(tg + kColDz, tg + kColAh + 8, b + (512 >> 4), ido);
+        mma_ts<1>(tg + kColDz, tg + kColAh, b + (1024 >> 4), ido);
+        mma_ts<1>(tg + kColDz, tg + kColAh + 8, b + (1536 >> 4), ido);
+        if (TANGENTS) {
+            mma_ts<0>(tg + kColDv, tg + kColAv, b, ido);
+            mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + (512 >> 4), ido);
         }
     }
     tc_commit(bar);
@@ -625,56 +673,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             // ---- take this row's record from the producer ----
             float x0, x1, R = 1.0f, p0 = 1.0f;
             mbar_wait(smem_u32(&S.full[sl]), use & 1u);
-            {
-                const float (*f)[kTile] = S.slot[sl];
-                uint32_t c[12];
-#pragma unroll
-                for (int j = 0; j < 11; ++j) c[j] = __float_as_uint(f[kFPe + j][row]);
-                c[11] = 0u;
-                tmem_st8(tg + kColA1 + 4, c);
-                tmem_st4(tg + kColA1 + 12, c[8], c[9], c[10], c[11]);
-                x0 = f[kFX][row]; x1 = f[kFX + 1][row];
-                if (MODE == kModeSample) p0 = f[kFP0][row];
-            }
+            const float (*f)[kTile] = S.slot[sl];
+            x0 = f[kFX][row]; x1 = f[kFX + 1][row];
+            if (MODE == kModeSample) p0 = f[kFP0][row];
             const float theta_o = x0;
-            if (MODE != kModePdf) {          // pdf mode reads the rest of the record at the end of the tile
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
-            }
 
 #pragma unroll 1
             for (int t = 0; t < P.T; ++t) {
                 const float tf = (float)t / (float)P.T;
                 const float alpha = (MODE == kModePdf) ? 1.0f - tf : tf;
-                // ---- state -> A1 columns 0..3 (hi parts, then lo parts); tangent seeds -> A_u, A_v chunk 0 ----
+                // ---- first-layer operand A1 (over A_h): state hi/lo parts in columns 0..3, PE5(wi) from the record in
+                //      4..15; tangent seeds -> A_u, A_v chunk 0 ----
                 {
+                    uint32_t a1[16];
+#pragma unroll
+                    for (int j = 0; j < 11; ++j) a1[4 + j] = __float_as_uint(f[kFPe + j][row]);
+                    a1[15] = 0u;
+                    if (MODE != kModePdf && t == P.T - 1) {      // last read of the record: hand the slot back
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
+                    }
                     float s0, s1, s2v, s3;
                     if (DOMAIN == kDisk) { s0 = x0; s1 = x1; s2v = alpha; s3 = 0.0f; }
                     else { __sincosf(x1, &s1, &s2v); s0 = x0; s3 = alpha; }
                     const uint32_t c01 = pack_h2(s0, s1), c23 = pack_h2(s2v, s3);
                     const uint32_t l01 = pack_h2(s0 - h2_lo(c01), s1 - h2_hi(c01));
                     const uint32_t l23 = pack_h2(s2v - h2_lo(c23), s3 - h2_hi(c23));
+                    uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // d/dx0 (d/dtheta): k = 0
+                    uint32_t ev[8] = {0x3C000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // disk d/dx1: k = 1
                     if (DOMAIN == kDisk) {
                         // k: x0_hi x1_hi | a_hi a_lo | x0_lo x1_lo | 0 0
-                        tmem_st4(tg + kColA1, c01, (c23 & 0xffffu) | (l23 << 16), l01, 0u);
-                        if (TANGENTS) {
-                            const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx0: k = 0
-                            const uint32_t ev[8] = {0x3C000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};      // d/dx1: k = 1
-                            tmem_st8(tg + kColA + 16, eu);
-                            tmem_st8(tg + kColA + 32, ev);
-                        }
+                        a1[0] = c01; a1[1] = (c23 & 0xffffu) | (l23 << 16); a1[2] = l01; a1[3] = 0u;
                     } else {
                         // k: th_hi sin_hi | cos_hi a_hi | th_lo sin_lo | cos_lo a_lo
-                        tmem_st4(tg + kColA1, c01, c23, l01, l23);
-                        if (TANGENTS) {
-                            // d/dtheta: k = 0.  d/dphi: d(sin) = cos on k = 1, d(cos) = -sin on k = 2 (hi parts), lo
-                            // parts on k = 5, 6 (the weight image repeats W1[:,1], W1[:,2] there)
-                            const uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-                            const uint32_t ev[8] = {c23 << 16, (c01 >> 16) ^ 0x8000u, l23 << 16, (l01 >> 16) ^ 0x8000u,
-                                                    0u, 0u, 0u, 0u};
-                            tmem_st8(tg + kColA + 16, eu);
-                            tmem_st8(tg + kColA + 32, ev);
-                        }
+                        a1[0] = c01; a1[1] = c23; a1[2] = l01; a1[3] = l23;
+                        // d/dphi: d(sin) = cos on k = 1, d(cos) = -sin on k = 2 (hi parts), lo parts on k = 5, 6 (the
+                        // weight image repeats W1[:,1], W1[:,2] there)
+                        ev[0] = c23 << 16; ev[1] = (c01 >> 16) ^ 0x8000u; ev[2] = l23 << 16; ev[3] = (l01 >> 16) ^ 0x8000u;
+                    }
+                    tmem_st8(tg + kColA1, a1);
+                    tmem_st8(tg + kColA1 + 8, a1 + 8);
+                    if (TANGENTS) {
+                        tmem_st8(tg + kColAu, eu);
+                        tmem_st8(tg + kColAv, ev);
                     }
                 }
                 publish_and_issue<TANGENTS>(g, q, 0, NH, tg_mma, w_base, bar_d);
@@ -684,21 +725,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 for (int l = 0; l < NH; ++l) {
                     mbar_wait(bar_d, pd); pd ^= 1u;
                     tc_fence_after();
-                    float za[16], ua[TANGENTS ? 16 : 1], va[TANGENTS ? 16 : 1];
-                    float zb[16], ub[TANGENTS ? 16 : 1], vb[TANGENTS ? 16 : 1];
-                    tmem_ld16(tg + kColD, za);
-                    if (TANGENTS) { tmem_ld16(tg + kColD + 32, ua); tmem_ld16(tg + kColD + 64, va); }
+                    float za[16], zb[16];
+                    uint32_t ua[TANGENTS ? 8 : 1], va[TANGENTS ? 8 : 1], ub[TANGENTS ? 8 : 1], vb[TANGENTS ? 8 : 1];
+                    tmem_ld16(tg + kColDz, za);
+                    if (TANGENTS) { tmem_ld8_pack16(tg + kColDu, ua); tmem_ld8_pack16(tg + kColDv, va); }
                     tc_wait_ld();
-                    tmem_ld16(tg + kColD + 16, zb);            // second half streams in under the first half's math
-                    if (TANGENTS) { tmem_ld16(tg + kColD + 32 + 16, ub); tmem_ld16(tg + kColD + 64 + 16, vb); }
+                    tmem_ld16(tg + kColDz + 16, zb);           // second half streams in under the first half's math
+                    if (TANGENTS) { tmem_ld8_pack16(tg + kColDu + 16, ub); tmem_ld8_pack16(tg + kColDv + 16, vb); }
                     uint32_t ph[8], pu[8], pv[8];
                     activate16<TANGENTS, ACT>(za, ua, va, ph, pu, pv);
-                    tmem_st8(tg + kColA, ph);
-                    if (TANGENTS) { tmem_st8(tg + kColA + 16, pu); tmem_st8(tg + kColA + 32, pv); }
+                    tmem_st8(tg + kColAh, ph);
+                    if (TANGENTS) { tmem_st8(tg + kColAu, pu); tmem_st8(tg + kColAv, pv); }
                     tc_wait_ld();
                     activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
-                    tmem_st8(tg + kColA + 8, ph);
-                    if (TANGENTS) { tmem_st8(tg + kColA + 16 + 8, pu); tmem_st8(tg + kColA + 32 + 8, pv); }
+                    tmem_st8(tg + kColAh + 8, ph);
+                    if (TANGENTS) { tmem_st8(tg + kColAu + 8, pu); tmem_st8(tg + kColAv + 8, pv); }
                     publish_and_issue<TANGENTS>(g, q, l + 1, NH, tg_mma, w_base, bar_d);
                 }
 
@@ -706,8 +747,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 mbar_wait(bar_d, pd); pd ^= 1u;
                 tc_fence_after();
                 float d0, d1, du0 = 0.f, du1 = 0.f, dv0 = 0.f, dv1 = 0.f;
-                tmem_ld2(tg + kColD, d0, d1);
-                if (TANGENTS) { tmem_ld2(tg + kColD + 32, du0, du1); tmem_ld2(tg + kColD + 64, dv0, dv1); }
+                tmem_ld2(tg + kColDz, d0, d1);
+                if (TANGENTS) { tmem_ld2(tg + kColDu, du0, du1); tmem_ld2(tg + kColDv, dv0, dv1); }
                 tc_wait_ld();
                 if (TANGENTS) {
                     const float j00 = fmaf(step, du0, 1.0f), j01 = step * dv0;
@@ -722,7 +763,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             if (MODE == kModeSample) {
                 if (valid) store_sample<true>(P, i, x0, x1, p0 * R);
             } else if (MODE == kModePdf) {
-                const float (*f)[kTile] = S.slot[sl];
                 float bp[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) bp[j] = f[kFBp + j][row];
