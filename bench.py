@@ -169,6 +169,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm runs on rank 0 alone and is meant
+        # to use every host thread (the OpenMP runtime reads the variable when the oracle library is first loaded)
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
         vals = []
         for _ in range(args.warmup and 1):
             cpu_leg(args.workload, T, 2.0)
