@@ -453,10 +453,11 @@ __device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, 
 // 1..NH-1: hidden layer, NH: output layer (N = 16, fp32 accumulators throughout).
 // Order: u, z, v -- A_u is read first and D_v (which overlaps A_u) is written last.
 template <bool TANGENTS>
-__device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint32_t w_base, uint32_t bar) {
+__device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint64_t b_hid0, uint64_t b_out, uint32_t bar) {
     constexpr uint32_t idz = make_idesc(32, true), idt = make_idesc(32, false), ido = make_idesc(16, true);
     if (type < NH) {
-        const uint64_t b = make_b_desc(w_base + 4096u * type, 512, 128);
+        // layer images are 4096 B apart: bump the descriptor's 16-byte-granular address field (no carry: smem < 256 KB)
+        const uint64_t b = b_hid0 + ((uint64_t)(uint32_t)type << 8);
         const uint32_t a = tg + (type == 0 ? kColA1 : kColAh);
         if (TANGENTS) {
             mma_ts<0>(tg + kColDu, tg + kColAu, b, idt);
@@ -471,7 +472,7 @@ __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint3
             if (type != 0) mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + (1024 >> 4), idt);
         }
     } else {                                        // output layer, N = 16
-        const uint64_t b = make_b_desc(w_base + 4096u * NH, 256, 128);
+        const uint64_t b = b_out;
         if (TANGENTS) {
             mma_ts<0>(tg + kColDu, tg + kColAu, b, ido);
             mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + (512 >> 4), ido);
@@ -491,13 +492,13 @@ __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint3
 // Hand the freshly written A operands to the tensor core: all 128 threads' TMEM stores must have landed
 // before one elected lane issues the round.
 template <bool TANGENTS>
-__device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH, uint32_t tg_mma, uint32_t w_base,
-                                                  uint32_t bar) {
+__device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH, uint32_t tg_mma, uint64_t b_hid0,
+                                                  uint64_t b_out, uint32_t bar) {
     tc_wait_st();
     tc_fence_before();
     group_sync(g);
     if (q == 0) {
-        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS>(type, NH, tg_mma, w_base, bar); }
+        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS>(type, NH, tg_mma, b_hid0, b_out, bar); }
     }
 }
 
@@ -657,6 +658,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         const uint32_t tg = tg_mma + ((uint32_t)(q * 32) << 16);                 // this warp's 32-lane window
         const uint32_t bar_d = smem_u32(&S.d_ready[g]);
         const uint32_t w_base = smem_u32(S.w16);
+        const uint64_t b_hid0 = make_b_desc(w_base, 512, 128);                   // first / hidden layers: N = 32 rows
+        const uint64_t b_out = make_b_desc(w_base + 4096u * NH, 256, 128);      // output layer: N = 16 rows
         uint32_t pd = 0;
         const float inv_t = (float)(1.0 / (double)P.T);
         const float step = (MODE == kModePdf) ? -inv_t : inv_t;
@@ -718,7 +721,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                         tmem_st8(tg + kColAv, ev);
                     }
                 }
-                publish_and_issue<TANGENTS>(g, q, 0, NH, tg_mma, w_base, bar_d);
+                publish_and_issue<TANGENTS>(g, q, 0, NH, tg_mma, b_hid0, b_out, bar_d);
 
                 // ---- activation rounds: layer 1 and the hidden layers share one instruction stream ----
 #pragma unroll 1
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                     activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
                     tmem_st8(tg + kColAh + 8, ph);
                     if (TANGENTS) { tmem_st8(tg + kColAu + 8, pu); tmem_st8(tg + kColAv + 8, pv); }
-                    publish_and_issue<TANGENTS>(g, q, l + 1, NH, tg_mma, w_base, bar_d);
+                    publish_and_issue<TANGENTS>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, bar_d);
                 }
 
                 // ---- output round: d, dd/dx0, dd/dx1 ----
