@@ -73,7 +73,13 @@ constexpr int kGroups = BSDFDIFF_TC_GROUPS;
 constexpr int kWorkerThreads = kGroups * 128;
 constexpr int kProducerWarps = 4;                  // one 128-thread producer group: thread <-> query row of a tile
 constexpr int kTcThreads = kWorkerThreads + 32 * kProducerWarps;
-constexpr int kSlots = kGroups + 2;                // prologue ring: every group holds its slot for the whole tile (PE5 is
+#ifndef BSDFDIFF_TC_SLOTS
+#define BSDFDIFF_TC_SLOTS (BSDFDIFF_TC_GROUPS + 2)
+#endif
+#ifndef BSDFDIFF_TC_BACKOFF_NS
+#define BSDFDIFF_TC_BACKOFF_NS 2000
+#endif
+constexpr int kSlots = BSDFDIFF_TC_SLOTS;                // prologue ring: every group holds its slot for the whole tile (PE5 is
                                                    // re-read each step), the producer runs up to two tiles ahead
 // per-query record handed from the producer to the worker thread of the same row (field-major in shared memory,
 // slot[field][row], so both sides access consecutive words)
@@ -95,6 +101,7 @@ constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 64, kColAh = 96, kC
 constexpr int kColA1 = kColAh;
 constexpr int kTmemCols = 512;
 static_assert(kGroups * kColsPerGroup <= kTmemCols, "TMEM budget");
+static_assert(kSlots > kGroups && kSlots < 2 * kGroups + 1, "slot ring: one wrap per worker iteration at most");
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -202,14 +209,25 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(taddr) : "memory");
     a = __uint_as_float(x); b = __uint_as_float(y);
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
-                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
                  ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// Eight operand words of this thread's row.  Issued as two .x4 stores: measured on B200, an .x8 (or .x16) store
+// holds the issuing warp ~20-45 cycles, an .x4 store ~5 (profiles/microbench/mma_issue: 6 x .x8 = 130-300 cycles,
+// 12 x .x4 = 56 cycles for the same bytes).
+#ifndef BSDFDIFF_TC_ST_X8
+#define BSDFDIFF_TC_ST_X8 0
+#endif
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    if (BSDFDIFF_TC_ST_X8) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                     ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                     : "memory");
+    } else {
+        tmem_st4(taddr, r[0], r[1], r[2], r[3]);
+        tmem_st4(taddr + 4, r[4], r[5], r[6], r[7]);
+    }
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -605,13 +623,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         };
         bool valid = false, valid_n = false;
         long long i = 0, i_n = 0;
+        int sl = 0;                                         // ring position of tile k: k % kSlots, lap k / kSlots
+        uint32_t use = 0;
         if (my_tiles > 0) { i = index_of(0, valid); raw_load<MODE>(P, i, cur); }
 #pragma unroll 1
         for (long long k = 0; k < my_tiles; ++k) {
             if (k + 1 < my_tiles) { i_n = index_of(k + 1, valid_n); raw_load<MODE>(P, i_n, nxt); }
-            const int sl = (int)(k % kSlots);
-            const uint32_t use = (uint32_t)(k / kSlots);
-
             // conditioning in domain coordinates (brdf_measured_disk.py:66-67, brdf_measured_spherical.py:76-77)
             float w0, w1, wiz = cur.wc;
             if (P.epilogue == kEpiRaw || P.epilogue == kEpiDisk) { w0 = cur.wa; w1 = cur.wb; }
@@ -634,7 +651,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 if (MODE == kModeSample) p0 = __expf(base_logprob_fast<DOMAIN>(bp, x0, x1));
             }
 
-            mbar_wait<2000>(smem_u32(&S.empty[sl]), (use & 1u) ^ 1u);   // the group that used this slot last has read it
+            mbar_wait<BSDFDIFF_TC_BACKOFF_NS>(smem_u32(&S.empty[sl]), (use & 1u) ^ 1u);   // the group that used this slot last has read it
             float (*f)[kTile] = S.slot[sl];
 #pragma unroll
             for (int j = 0; j < 11; ++j) f[kFPe + j][row] = __uint_as_float(c[j]);
@@ -649,6 +666,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.full[sl]));      // release: the stores above are visible to the waiters
             cur = nxt; i = i_n; valid = valid_n;
+            if (++sl == kSlots) { sl = 0; ++use; }
         }
     } else {
         // =========================== workers ===========================================================
@@ -659,8 +677,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         const uint32_t bar_d = smem_u32(&S.d_ready[g]);
         const uint32_t w_base = smem_u32(S.w16);
         const uint64_t b_hid0 = make_b_desc(w_base, 512, 128);                   // first / hidden layers: N = 32 rows
-        const uint64_t b_out = make_b_desc(w_base + 4096u * NH, 256, 128);      // output layer: N = 16 rows
+        uint64_t b_out = make_b_desc(w_base + 4096u * NH, 256, 128);            // output layer: N = 16 rows
+        asm volatile("" : "+l"(b_out));                                         // keep it in registers (no per-round rebuild)
         uint32_t pd = 0;
+        int sl = g;                                         // ring position / lap of this group's current tile
+        uint32_t use = 0;
         const float inv_t = (float)(1.0 / (double)P.T);
         const float step = (MODE == kModePdf) ? -inv_t : inv_t;
         if (q == 0) mbar_wait(smem_u32(&S.w_bar), 0);                           // weights have landed in smem
@@ -670,8 +691,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             const long long i_raw = (blockIdx.x + k * gridDim.x) * kTile + row;
             const bool valid = i_raw < P.n;
             const long long i = valid ? i_raw : (P.n - 1);
-            const int sl = (int)(k % kSlots);
-            const uint32_t use = (uint32_t)(k / kSlots);
 
             // ---- take this row's record from the producer ----
             float x0, x1, R = 1.0f, p0 = 1.0f;
@@ -777,6 +796,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             } else {
                 if (valid) reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
             }
+            sl += kGroups;
+            if (sl >= kSlots) { sl -= kSlots; ++use; }
         }
     }
 

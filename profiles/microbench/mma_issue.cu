@@ -47,6 +47,15 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -157,6 +166,35 @@ __global__ void __launch_bounds__(128, 1) probe(int test, int k, int N, Res* out
             t_st += c1 - c0; t_w += c2 - c1; t_f += c3 - c2;
         }
         if (threadIdx.x == 0) { out->c[0] = t_st / REPS; out->c[1] = t_w / REPS; out->c[2] = t_f / REPS; }
+    } else if (test == 6 || test == 7) {
+        // same bytes as 6 x st.x8: 3 x st.x16 (test 6) or 12 x st.x4 (test 7); k warps active
+        long long t_st = 0, t_w = 0;
+        if (warp < k) {
+            for (int rep = 0; rep < REPS; ++rep) {
+                const long long c0 = clock64();
+                if (test == 6) { tmem_st16(tw + 256, v); tmem_st16(tw + 272, v); tmem_st16(tw + 288, v); }
+                else { for (int i = 0; i < 12; ++i) tmem_st4(tw + 256 + 4 * i, v); }
+                const long long c1 = clock64();
+                tc_wait_st();
+                const long long c2 = clock64();
+                t_st += c1 - c0; t_w += c2 - c1;
+            }
+            if (threadIdx.x == 0) { out->c[0] = t_st / REPS; out->c[1] = t_w / REPS; }
+        }
+    } else if (test == 8) {
+        // 6 x st.x8 with k warps active (test 4 has all four)
+        long long t_st = 0, t_w = 0;
+        if (warp < k) {
+            for (int rep = 0; rep < REPS; ++rep) {
+                const long long c0 = clock64();
+                for (int i = 0; i < 6; ++i) tmem_st8(tw + 256 + 8 * i, v);
+                const long long c1 = clock64();
+                tc_wait_st();
+                const long long c2 = clock64();
+                t_st += c1 - c0; t_w += c2 - c1;
+            }
+            if (threadIdx.x == 0) { out->c[0] = t_st / REPS; out->c[1] = t_w / REPS; }
+        }
     } else if (test == 5) {
         long long t_f = 0, t_ld = 0;
         uint32_t a[16], c[16], d[16], s = 0;
@@ -200,6 +238,9 @@ int main() {
     run(2, 0, 32); printf("mbarrier arrive -> peer wake: %lld cyc\n", h.c[0]);
     run(3, 0, 32); printf("bar.sync(128): %lld cyc\n", h.c[0]);
     for (int k : {1, 3, 6}) { run(4, k, 32); printf("st.x8 x%d: issue %lld | wait::st %lld | fence::before %lld\n", k, h.c[0], h.c[1], h.c[2]); }
+    for (int k : {1, 4}) { run(8, k, 32); printf("6 x st.x8  (%d warps): issue %lld | wait::st %lld\n", k, h.c[0], h.c[1]); }
+    for (int k : {1, 4}) { run(6, k, 32); printf("3 x st.x16 (%d warps): issue %lld | wait::st %lld\n", k, h.c[0], h.c[1]); }
+    for (int k : {1, 4}) { run(7, k, 32); printf("12 x st.x4 (%d warps): issue %lld | wait::st %lld\n", k, h.c[0], h.c[1]); }
     for (int k : {1, 2, 3}) { run(5, k, 32); printf("fence::after %lld | ld.x16 x%d + wait::ld %lld\n", h.c[0], k, h.c[1]); }
     return 0;
 }
