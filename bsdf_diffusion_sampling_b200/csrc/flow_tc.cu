@@ -427,9 +427,12 @@ struct TcSmem {
     __align__(16) float bb1[16];
     __align__(16) float bwot[16 * 4];
     __align__(16) float bbo[4];
-    __align__(128) unsigned char w16[2 * (32 * 32 + 5 * 32 * 32 + 16 * 32) * 2];   // hi+lo images, <= 6 hidden layers
     __align__(16) float slot[kSlots][kFields][kTile];
+    __align__(128) unsigned char w16[128];    // hi+lo operand images of every layer: dynamic tail, hdr->f16_bytes long
 };
+static inline size_t tc_smem_bytes(int H, int n_hidden) {
+    return offsetof(TcSmem, w16) + sizeof(__half) * (size_t)f16_image_halves(H, n_hidden);
+}
 
 // base net p = Wo silu(W1 PE3(e) + b1) + bo from the shared-memory copy (rendering/utils/model.py:382-386)
 __device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, float p[4]) {
@@ -470,38 +473,64 @@ __device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, 
 // tangents use hi only.  type 0: first layer (tangent seeds are K=16 operands in A_u/A_v chunk 0),
 // 1..NH-1: hidden layer, NH: output layer (N = 16, fp32 accumulators throughout).
 // Order: u, z, v -- A_u is read first and D_v (which overlaps A_u) is written last.
-template <bool TANGENTS>
-__device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint64_t b_hid0, uint64_t b_out, uint32_t bar) {
-    constexpr uint32_t idz = make_idesc(32, true), idt = make_idesc(32, false), ido = make_idesc(16, true);
+template <bool TANGENTS, int H>
+__device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint64_t b_first, uint64_t b_out, uint32_t bar) {
+    constexpr uint32_t idz = make_idesc(H, true), idt = make_idesc(H, false), ido = make_idesc(16, true);
+    // descriptor address units are 16 bytes.  One K chunk (16 halves = two core-matrix columns) of an [N x K] image
+    // is 2 * N * 16 bytes; the LO image follows the HI image.
+    constexpr uint32_t kChunk = (2u * H * 16u) >> 4;                // K-chunk stride of an N = H operand
+    constexpr uint32_t kLoFirst = (H * 32u * 2u) >> 4;              // first layer: [H x 32] halves
+    constexpr uint32_t kLoHid = (H * H * 2u) >> 4;                  // hidden layer: [H x H] halves
+    constexpr uint32_t kFirstBytes = 2u * H * 32u * 2u, kHidBytes = 2u * H * H * 2u;   // hi + lo
+    constexpr uint32_t kChunkOut = (2u * 16u * 16u) >> 4, kLoOut = (16u * H * 2u) >> 4;
+    static_assert(!TANGENTS || H == 32, "tangent rounds exist for the 32-wide sampler nets only");
     if (type < NH) {
-        // layer images are 4096 B apart: bump the descriptor's 16-byte-granular address field (no carry: smem < 256 KB)
-        const uint64_t b = b_hid0 + ((uint64_t)(uint32_t)type << 8);
+        // layer images follow each other: bump the descriptor's 16-byte-granular address field (no carry: smem < 256 KB)
+        const uint64_t b = (type == 0) ? b_first
+                                       : b_first + (uint64_t)((kFirstBytes >> 4) + (uint32_t)(type - 1) * (kHidBytes >> 4));
         const uint32_t a = tg + (type == 0 ? kColA1 : kColAh);
+        const uint32_t lo = (type == 0) ? kLoFirst : kLoHid;
         if (TANGENTS) {
             mma_ts<0>(tg + kColDu, tg + kColAu, b, idt);
-            if (type != 0) mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + (1024 >> 4), idt);
+            if (type != 0) mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunk, idt);
         }
-        mma_ts<0>(tg + kColDz, a, b, idz);
-        mma_ts<1>(tg + kColDz, a + 8, b + (1024 >> 4), idz);
-        mma_ts<1>(tg + kColDz, a, b + (2048 >> 4), idz);
-        mma_ts<1>(tg + kColDz, a + 8, b + (3072 >> 4), idz);
+        if (H == 32) {
+            mma_ts<0>(tg + kColDz, a, b, idz);
+            mma_ts<1>(tg + kColDz, a + 8, b + kChunk, idz);
+            mma_ts<1>(tg + kColDz, a, b + lo, idz);
+            mma_ts<1>(tg + kColDz, a + 8, b + lo + kChunk, idz);
+        } else {
+            mma_ts<0>(tg + kColDz, a, b, idz);
+            mma_ts<1>(tg + kColDz, a + 8, b + kChunk, idz);
+            if (type != 0) {
+#pragma unroll
+                for (int c = 2; c < H / 16; ++c) mma_ts<1>(tg + kColDz, a + 8 * c, b + c * kChunk, idz);
+            }
+            mma_ts<1>(tg + kColDz, a, b + lo, idz);
+            mma_ts<1>(tg + kColDz, a + 8, b + lo + kChunk, idz);
+            if (type != 0) {
+#pragma unroll
+                for (int c = 2; c < H / 16; ++c) mma_ts<1>(tg + kColDz, a + 8 * c, b + lo + c * kChunk, idz);
+            }
+        }
         if (TANGENTS) {
             mma_ts<0>(tg + kColDv, tg + kColAv, b, idt);
-            if (type != 0) mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + (1024 >> 4), idt);
+            if (type != 0) mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + kChunk, idt);
         }
     } else {                                        // output layer, N = 16
         const uint64_t b = b_out;
         if (TANGENTS) {
             mma_ts<0>(tg + kColDu, tg + kColAu, b, ido);
-            mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + (512 >> 4), ido);
+            mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunkOut, ido);
         }
         mma_ts<0>(tg + kColDz, tg + kColAh, b, ido);
-        mma_ts<1>(tg + kColDz, tg + kColAh + 8, b + (512 >> 4), ido);
-        mma_ts<1>(tg + kColDz, tg + kColAh, b + (1024 >> 4), ido);
-        mma_ts<1>(tg + kColDz, tg + kColAh + 8, b + (1536 >> 4), ido);
+#pragma unroll
+        for (int c = 1; c < H / 16; ++c) mma_ts<1>(tg + kColDz, tg + kColAh + 8 * c, b + c * kChunkOut, ido);
+#pragma unroll
+        for (int c = 0; c < H / 16; ++c) mma_ts<1>(tg + kColDz, tg + kColAh + 8 * c, b + kLoOut + c * kChunkOut, ido);
         if (TANGENTS) {
             mma_ts<0>(tg + kColDv, tg + kColAv, b, ido);
-            mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + (512 >> 4), ido);
+            mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + kChunkOut, ido);
         }
     }
     tc_commit(bar);
@@ -509,14 +538,14 @@ __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint6
 
 // Hand the freshly written A operands to the tensor core: all 128 threads' TMEM stores must have landed
 // before one elected lane issues the round.
-template <bool TANGENTS>
+template <bool TANGENTS, int H>
 __device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH, uint32_t tg_mma, uint64_t b_hid0,
                                                   uint64_t b_out, uint32_t bar) {
     tc_wait_st();
     tc_fence_before();
     group_sync(g);
     if (q == 0) {
-        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS>(type, NH, tg_mma, b_hid0, b_out, bar); }
+        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS, H>(type, NH, tg_mma, b_hid0, b_out, bar); }
     }
 }
 
@@ -560,9 +589,10 @@ __device__ __forceinline__ void raw_load(const FlowParams& P, long long i, RawIn
 //                 serial FMA chains); on its own warps it fills the issue slots the workers leave idle while they
 //                 wait for MMAs instead of adding ~1/3 to every tile's critical path (profiles/r1d vs r1h).
 // ------------------------------------------------------------------------------------------------
-template <int DOMAIN, int MODE, int ACT>
+template <int DOMAIN, int MODE, int ACT, int H>
 __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams P) {
     constexpr bool TANGENTS = (MODE != kModeForward);
+    static_assert(H == 32 || (H == 64 && !TANGENTS), "64-wide nets: forward-only (reflow teacher) rounds");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     // warp index through a shuffle so the compiler can prove it warp-uniform: TMEM addresses and MMA
@@ -676,8 +706,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         const uint32_t tg = tg_mma + ((uint32_t)(q * 32) << 16);                 // this warp's 32-lane window
         const uint32_t bar_d = smem_u32(&S.d_ready[g]);
         const uint32_t w_base = smem_u32(S.w16);
-        const uint64_t b_hid0 = make_b_desc(w_base, 512, 128);                   // first / hidden layers: N = 32 rows
-        uint64_t b_out = make_b_desc(w_base + 4096u * NH, 256, 128);            // output layer: N = 16 rows
+        const uint64_t b_hid0 = make_b_desc(w_base, H * 16, 128);                // first / hidden layers: N = H rows
+        uint64_t b_out = make_b_desc(w_base + 2u * H * 32u * 2u + (uint32_t)(NH - 1) * (2u * H * H * 2u), 256, 128);   // N = 16
         asm volatile("" : "+l"(b_out));                                         // keep it in registers (no per-round rebuild)
         uint32_t pd = 0;
         int sl = g;                                         // ring position / lap of this group's current tile
@@ -740,13 +770,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                         tmem_st8(tg + kColAv, ev);
                     }
                 }
-                publish_and_issue<TANGENTS>(g, q, 0, NH, tg_mma, b_hid0, b_out, bar_d);
+                publish_and_issue<TANGENTS, H>(g, q, 0, NH, tg_mma, b_hid0, b_out, bar_d);
 
                 // ---- activation rounds: layer 1 and the hidden layers share one instruction stream ----
 #pragma unroll 1
                 for (int l = 0; l < NH; ++l) {
                     mbar_wait(bar_d, pd); pd ^= 1u;
                     tc_fence_after();
+                    if (H != 32) {
+                        // wide forward-only round: H / 16 chunks of 16 neurons, the next chunk's load in flight
+                        float zc[2][16];
+                        uint32_t ph[8];
+                        tmem_ld16(tg + kColDz, zc[0]);
+#pragma unroll
+                        for (int c = 0; c < H / 16; ++c) {
+                            tc_wait_ld();
+                            if (c + 1 < H / 16) tmem_ld16(tg + kColDz + 16 * (c + 1), zc[(c + 1) & 1]);
+                            activate16<false, ACT>(zc[c & 1], nullptr, nullptr, ph, nullptr, nullptr);
+                            tmem_st8(tg + kColAh + 8 * c, ph);
+                        }
+                        publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, bar_d);
+                        continue;
+                    }
                     float za[16], zb[16];
                     uint32_t ua[TANGENTS ? 8 : 1], va[TANGENTS ? 8 : 1], ub[TANGENTS ? 8 : 1], vb[TANGENTS ? 8 : 1];
                     tmem_ld16(tg + kColDz, za);
@@ -762,7 +807,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                     activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
                     tmem_st8(tg + kColAh + 8, ph);
                     if (TANGENTS) { tmem_st8(tg + kColAu + 8, pu); tmem_st8(tg + kColAv + 8, pv); }
-                    publish_and_issue<TANGENTS>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, bar_d);
+                    publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, bar_d);
                 }
 
                 // ---- output round: d, dd/dx0, dd/dx1 ----
@@ -811,7 +856,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     }
 }
 
-template <int DOMAIN, int MODE, int ACT>
+template <int DOMAIN, int MODE, int ACT, int H>
 static int launch_tc_t(const FlowParams& P, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
@@ -820,28 +865,34 @@ static int launch_tc_t(const FlowParams& P, cudaStream_t stream) {
     long long grid = sms;
     if (grid > tiles) grid = tiles;
     if (grid < 1) return 0;
-    static bool attr_set = false;            // per instantiation; benign if two host threads race (same value)
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(flow_tc_kernel<DOMAIN, MODE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(TcSmem)) != cudaSuccess) return -3;
-        attr_set = true;
+    const size_t smem = tc_smem_bytes(H, P.n_hidden);
+    if (smem > 227u * 1024u) return -2;
+    static size_t attr_bytes = 0;            // per instantiation; benign if two host threads race (monotone)
+    if (smem > attr_bytes) {
+        if (cudaFuncSetAttribute(flow_tc_kernel<DOMAIN, MODE, ACT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem) != cudaSuccess) return -3;
+        attr_bytes = smem;
     }
-    flow_tc_kernel<DOMAIN, MODE, ACT><<<(unsigned)grid, kTcThreads, sizeof(TcSmem), stream>>>(P);
+    flow_tc_kernel<DOMAIN, MODE, ACT, H><<<(unsigned)grid, kTcThreads, smem, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 template <int DOMAIN, int ACT>
 static int launch_tc_m(const FlowParams& P, cudaStream_t stream) {
+    if (P.hidden == 64) {                     // reflow teacher nets (NN_cond_pos_spherical_complicate): forward only
+        if (P.mode != kModeForward) return -2;
+        return launch_tc_t<DOMAIN, kModeForward, ACT, 64>(P, stream);
+    }
     switch (P.mode) {
-        case kModeSample: return launch_tc_t<DOMAIN, kModeSample, ACT>(P, stream);
-        case kModePdf: return launch_tc_t<DOMAIN, kModePdf, ACT>(P, stream);
-        default: return launch_tc_t<DOMAIN, kModeForward, ACT>(P, stream);
+        case kModeSample: return launch_tc_t<DOMAIN, kModeSample, ACT, 32>(P, stream);
+        case kModePdf: return launch_tc_t<DOMAIN, kModePdf, ACT, 32>(P, stream);
+        default: return launch_tc_t<DOMAIN, kModeForward, ACT, 32>(P, stream);
     }
 }
 
 // variant 1 = tc16 (tanh.approx activation), 2 = tc16 with fp32 exp-form activation (cross-check)
 int launch_tc(const FlowParams& P, cudaStream_t stream, int variant) {
-    if (P.hidden != 32 || P.n_hidden < 2 || P.n_hidden > 6) return -2;      // 64-wide nets: CUDA-core path
+    if ((P.hidden != 32 && P.hidden != 64) || P.n_hidden < 2 || P.n_hidden > 6) return -2;   // else: CUDA-core path
     if (P.domain == kDisk)
         return variant == 2 ? launch_tc_m<kDisk, 0>(P, stream) : launch_tc_m<kDisk, 1>(P, stream);
     return variant == 2 ? launch_tc_m<kSpherical, 0>(P, stream) : launch_tc_m<kSpherical, 1>(P, stream);
