@@ -276,10 +276,10 @@ def main():
     per_gpu_qps = n * args.steps / (ms * 1e-3)
     achieved = per_gpu_qps * F / 1e12
     # DRAM traffic of ONE launch from the committed ncu --set full capture of this exact configuration
-    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1h_ncu_tc16_disk_summary.txt); other configs: null
-    traffic = 424.68e6 if (args.workload == "disk" and n == 4096 * 4096 and args.precision == "tc16") else None
+    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1n_ncu_tc16_disk_summary.txt); other configs: null
+    traffic = 423.12e6 if (args.workload == "disk" and n == 4096 * 4096 and args.precision == "tc16") else None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1h_ncu_tc16_disk_summary.txt (bytes per launch)"
+                "traffic": traffic, "traffic_source": "profiles/r1n_ncu_tc16_disk_summary.txt (bytes per launch)"
                 if traffic else None, "peak_source": peak_src,
                 "kernel": "flow_tc_kernel" if args.precision == "tc16" else "flow_simt_kernel",
                 "flops_per_query": F, "avg_launch_ms": ms / args.steps,
