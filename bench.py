@@ -199,6 +199,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pkg.sharding.bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     layers, base = load_fixture(args.workload)
@@ -296,6 +297,8 @@ def main():
             "gpu_launches": args.steps, "checksum_pdf": checksum}
     if e2e:
         line["e2e"] = e2e
+    if numa is not None:
+        line["config"]["numa_node_rank0"] = numa
     if not args.no_cpu and world == 1:
         try:
             line["cpu_baseline"] = cpu_leg(args.workload, T)[0]
@@ -307,4 +310,21 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    # stdout when NCCL_DEBUG is VERSION/WARN), so file descriptor 1 is pointed at stderr for the whole run and the
+    # result line goes to the saved descriptor.
+    sys.stdout.flush()
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _emit = []
+    _print = print
+
+    def print(*a, **k):                                  # noqa: A001  (result lines only; everything else -> stderr)
+        _emit.append(" ".join(str(x) for x in a))
+
+    try:
+        main()
+    finally:
+        sys.stdout.flush()
+        for _l in _emit:
+            os.write(_real_stdout, (_l + "\n").encode())

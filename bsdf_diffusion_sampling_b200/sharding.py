@@ -18,6 +18,33 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin the calling process to the CPU cores of the NUMA node the GPU hangs off (PCI bus id ->
+    /sys/bus/pci/devices/<id>/numa_node -> node cpulist).  Pinned host buffers allocated afterwards land on that
+    node, so the host<->device copies of ``NeuralBSDFSampler.sample_host`` do not cross the inter-socket link when
+    several ranks stream at once.  Returns the node, or None when the topology is not exposed (single node, VM)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:                                  # noqa: BLE001  (best effort: never fail the caller)
+        return None
+
+
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     """Contiguous block [start, stop) of rank ``rank``: the first ``n % world`` ranks get one extra row."""
     if world < 1 or not (0 <= rank < world):
