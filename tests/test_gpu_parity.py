@@ -368,6 +368,39 @@ def test_cuda_graph_capture(pkg, prec):
     check_x(out[0].cpu().numpy(), z["x"], prec)
 
 
+def test_multi_material_wavefront(pkg):
+    """One wavefront with a material id per lane == the per-material calls on the lanes of each material."""
+    mats = []
+    disk_files = [f for f in GOLDEN_FILES if "disk_" in f.replace("\\", "/").split("/")[-1]]
+    assert len(disk_files) == 3
+    for path in disk_files:
+        flow, base, _ = O.load_material_npz(path)
+        mats.append(pkg.plugins.NeuralBSDFSampler("disk", pkg.weights.pack_flow_layers(flow.layers, "cuda"),
+                                                  pkg.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, "cuda")))
+    mm = pkg.plugins.MultiMaterialSampler(mats)
+    rng = np.random.default_rng(5)
+    n = 50_000
+    w = rng.normal(size=(n, 3)).astype(np.float32)
+    w[:, 2] = np.abs(w[:, 2]) + 0.05
+    wi = cu(w / np.linalg.norm(w, axis=1, keepdims=True))
+    x0 = cu(rng.normal(0, 0.3, (n, 2)).astype(np.float32))
+    mid = torch.from_numpy(rng.integers(0, 3, n)).cuda()
+    mid[:7] = 1                                            # a run of equal ids at the front
+    wo, pdf = mm.sample(wi, mid, x0=x0)
+    p2 = mm.pdf(wi, wo, mid)
+    for m, s in enumerate(mats):
+        sel = (mid == m).nonzero().squeeze(1)
+        wo_m, pdf_m = s.sample(wi[sel], x0=x0[sel])
+        assert torch.equal(wo[sel], wo_m) and torch.equal(pdf[sel], pdf_m)
+        assert torch.equal(p2[sel], s.pdf(wi[sel], wo_m))
+    # Philox path: deterministic for a given (seed, offset, ids); an id outside the table raises
+    a = mm.sample(wi, mid, seed=3, offset=8)
+    b = mm.sample(wi, mid, seed=3, offset=8)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    with pytest.raises(IndexError):
+        mm.sample(wi, mid + 1, seed=3)
+
+
 # ------------------------------------------------------------------------------------------------
 # 5. reflow (dosampling) and the tinycudann.Network shim
 # ------------------------------------------------------------------------------------------------

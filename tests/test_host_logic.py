@@ -105,6 +105,31 @@ def test_argument_validation_without_gpu(built_lib):
         built_lib.ops.sample(torch.zeros(4, 2), pf, torch.zeros(308), 4, x0=torch.zeros(4, 2))
 
 
+def test_multi_material_bucketing_without_gpu(built_lib):
+    """MultiMaterialSampler host logic: stable bucket order, counts, id range and kind checks (no kernel call)."""
+    P = built_lib.plugins
+    flow, base, _ = O.load_material_npz(DISK_FILE)
+    pf = built_lib.weights.pack_flow_layers(flow.layers, "cpu")
+    pb = built_lib.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, "cpu")
+    a, b = P.NeuralBSDFSampler("disk", pf, pb), P.NeuralBSDFSampler("disk", pf, pb, T=8)
+    mm = P.MultiMaterialSampler([a, b])
+    mid = torch.tensor([1, 0, 1, 1, 0, 0, 1], dtype=torch.int32)
+    order, counts = mm._buckets(mid)
+    assert counts == [3, 4]
+    assert order.tolist() == [1, 4, 5, 0, 2, 3, 6]                   # stable: wavefront order inside each bucket
+    with pytest.raises(IndexError):
+        mm._buckets(torch.tensor([0, 2]))
+    with pytest.raises(TypeError):
+        mm._buckets(torch.tensor([0.0, 1.0]))
+    with pytest.raises(ValueError):
+        P.MultiMaterialSampler([])
+    sflow, sbase, _ = O.load_material_npz(BSDF_FILE)
+    sph = P.NeuralBSDFSampler("bsdf", built_lib.weights.pack_flow_layers(sflow.layers, "cpu"),
+                              built_lib.weights.pack_base_arrays(sbase.w1, sbase.b1, sbase.wo, sbase.bo, "cpu"))
+    with pytest.raises(ValueError, match="share a plugin kind"):
+        P.MultiMaterialSampler([a, sph])
+
+
 def test_model_classes_load_reference_state_dict_keys(built_lib):
     m = built_lib.model
     flow, base, z = O.load_material_npz(DISK_FILE)
