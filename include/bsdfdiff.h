@@ -105,7 +105,10 @@ int bsdfdiff_pdf(int precision, int domain, int epilogue, int T, int64_t n,
 /* ---- forward-only flow (reflow "dosampling"): x_T = x0 + sum_t D(x_t, t/T | wi)/T, no pdf -------------------
  * wi: [n_wi,2] domain coords; query i uses wi[i / wi_repeat] (repeat_interleave without materialising it).
  * x0: [n,2] start state, or NULL to draw it from the base net (base_params required) with Philox;
- * out_x0 (optional) receives the start state. */
+ * out_x0 (optional) receives the start state.
+ * PREC_TC16 covers hidden = 32 (NN_cond_pos_simpler, disk reflow, T = 256) and hidden = 64 with up to 6 hidden layers
+ * (NN_cond_pos_spherical_complicate, learning_repo_cleanup/utils/model.py:449-477, spherical / bsdf reflow, T = 128):
+ * replaces the tcnn FullyFusedMLP loop of disk_domain_sampling.py:93-110 / spherical_domain_sampling.py:147-166. */
 int bsdfdiff_flow_forward(int precision, int domain, int T, int64_t n, const float* wi, int64_t wi_repeat,
                           const void* flow_packed, int hidden, int n_hidden, const float* base_params,
                           const float* x0, uint64_t seed, uint64_t offset, int64_t first_index,
