@@ -426,6 +426,32 @@ def test_reflow_forward_vs_reference(pkg, path, prec):
     assert err.max() <= 1e-4 if prec == "fp32" else np.quantile(err, 0.99) <= 2e-2
 
 
+@pytest.mark.parametrize("n_hidden", [2, 4, 6])
+@pytest.mark.parametrize("in_dim,domain", [(25, "disk"), (26, "spherical")])
+def test_wide_forward_tensor_core_vs_fp32(pkg, in_dim, domain, n_hidden):
+    """64-wide forward-only rounds on the tensor core (any depth the kernel accepts, both first-layer column maps,
+    ragged sizes) against the fp32 CUDA-core kernel of the same library on random bias-free SiLU nets."""
+    rng = np.random.default_rng(100 * n_hidden + in_dim)
+    H = 64
+    layers = [rng.normal(0, 1.2 / np.sqrt(in_dim), (H, in_dim)).astype(np.float32)]
+    layers += [rng.normal(0, 1.2 / np.sqrt(H), (H, H)).astype(np.float32) for _ in range(n_hidden - 1)]
+    layers += [rng.normal(0, 1.0 / np.sqrt(H), (2, H)).astype(np.float32)]
+    pf = pkg.weights.pack_flow_layers(layers, "cuda")
+    assert pf.hidden == 64 and pf.n_hidden == n_hidden
+    for n in (1, 127, 129, 20_000):
+        if domain == "disk":
+            wi = rng.uniform(-0.6, 0.6, (n, 2)).astype(np.float32)
+        else:
+            wi = np.stack([rng.uniform(0.05, 1.5, n), rng.uniform(-3.1, 3.1, n)], 1).astype(np.float32)
+        x0 = rng.normal(0, 0.4, (n, 2)).astype(np.float32)
+        a, _ = pkg.ops.flow_forward(cu(wi), pf, 16, x0=cu(x0), precision="tc16")
+        b, _ = pkg.ops.flow_forward(cu(wi), pf, 16, x0=cu(x0), precision="fp32")
+        err = (a - b).abs().cpu().numpy()
+        assert np.isfinite(err).all()
+        assert np.quantile(err, 0.99) <= 5e-3 and err.max() <= 5e-2, (n, float(err.max()))
+    assert pkg._lib.lib.bsdfdiff_debug_timeout_flag() == 0
+
+
 def test_dosampling_and_network_shim(pkg):
     flow, base, z = O.load_material_npz(DISK_FILE)
     m, r = pkg.model, pkg.reflow
