@@ -279,9 +279,11 @@ def main():
     # DRAM traffic of ONE launch from the committed ncu --set full capture of this exact configuration
     # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1n_ncu_tc16_disk_summary.txt); other configs: null
     traffic = 423.12e6 if (args.workload == "disk" and n == 4096 * 4096 and args.precision == "tc16") else None
+    traffic_src = "profiles/r1n_ncu_tc16_disk_summary.txt (bytes per launch)"
+    if args.workload == "spherical" and n == 4096 * 4096 and args.precision == "tc16":
+        traffic, traffic_src = 422.80e6, "profiles/r1n_ncu_tc16_spherical_summary.txt (bytes per launch)"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": "profiles/r1n_ncu_tc16_disk_summary.txt (bytes per launch)"
-                if traffic else None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src if traffic else None, "peak_source": peak_src,
                 "kernel": "flow_tc_kernel" if args.precision == "tc16" else "flow_simt_kernel",
                 "flops_per_query": F, "avg_launch_ms": ms / args.steps,
                 "hbm_algorithmic_bytes_per_query": 28, "hbm_achieved_gbs": per_gpu_qps * 28 / 1e9,
