@@ -53,6 +53,8 @@
 //   [ 96,112)  A_h / A1    fp16 operand of the hidden rounds; at every step start it is rewritten as the first-layer
 //                          operand A1 (cols 0..3 state, 4..15 PE5(wi) re-read from the tile's shared-memory record)
 //   [112,128)  A_v         fp16 operand
+// (BSDFDIFF_TC_GROUPS=5 builds a 96-column map with five tiles in flight -- v-tangent operand through shared memory --
+// which is bit-identical and no faster: DESIGN.md 4.1.)
 // A_u and D_v overlap so that a tile needs 128 instead of 144 columns (four tiles in flight, not three).  A round
 // issues its MMAs in the order  u (reads A_u) ; z (four MMAs) ; v (writes D_v):  tcgen05.mma instructions of one
 // thread execute in issue order, so A_u has been consumed five MMAs before the first write to D_v; threads only
@@ -91,14 +93,24 @@ constexpr int kFWiz = 18;                          // wi_z, wo (pdf-mode masks)
 constexpr int kFWo = 19;
 constexpr int kFields = 22;
 constexpr int kTile = 128;
-#ifdef BSDFDIFF_TC_NOALIAS
+#if BSDFDIFF_TC_GROUPS == 5
+// Five tiles in flight: 96 columns per tile.  The v-tangent operand goes through shared memory (SS-form MMA), A_h sits
+// inside D_u and A_u inside D_v; a round issues z (reads A_h), u (reads A_u, writes D_u over A_h), v (reads smem,
+// writes D_v over A_u) -- tcgen05.mma of one thread execute in issue order.  64-wide forward rounds: D_z 64 + A_h 32.
+constexpr bool kSmemAv = true;
+constexpr int kColsPerGroup = 96;
+constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 64, kColAh32 = 32, kColAh64 = 64, kColAv = 0;
+#elif defined(BSDFDIFF_TC_NOALIAS)
+constexpr bool kSmemAv = false;
 constexpr int kColsPerGroup = 144;
-constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 96, kColAh = 112, kColAv = 128;
+constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 96, kColAh32 = 112, kColAh64 = 112, kColAv = 128;
 #else
+constexpr bool kSmemAv = false;
 constexpr int kColsPerGroup = 128;
-constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 64, kColAh = 96, kColAv = 112;
+constexpr int kColDz = 0, kColDu = 32, kColDv = 64, kColAu = 64, kColAh32 = 96, kColAh64 = 96, kColAv = 112;
 #endif
-constexpr int kColA1 = kColAh;
+template <int H> __host__ __device__ constexpr int col_ah() { return H == 64 ? kColAh64 : kColAh32; }
+constexpr int kAvBytes = kTile * 64;                // one tile's v-tangent operand in shared memory: 128 rows x K = 32 halves
 constexpr int kTmemCols = 512;
 static_assert(kGroups * kColsPerGroup <= kTmemCols, "TMEM budget");
 static_assert(kSlots > kGroups && kSlots < 2 * kGroups + 1, "slot ring: one wrap per worker iteration at most");
@@ -185,6 +197,23 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(ACC) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T (A through a shared-memory descriptor)
+template <int ACC>
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "n"(ACC) : "memory");
+}
+// eight operand words (16 halves = two 8-half core-matrix rows) of this thread's row into the shared-memory A image:
+// K-major canonical layout, core column c at +c * 2048 bytes (16 row groups x 128 B)
+__device__ __forceinline__ void smem_st_a16(uint32_t row_addr, int chunk, const uint32_t* r) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_addr + (uint32_t)chunk * 2048u), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]) : "memory");
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(row_addr + (uint32_t)(chunk + 1) * 2048u), "r"(r[4]),
+                 "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -424,6 +453,7 @@ struct TcSmem {
     __align__(16) float bwot[16 * 4];
     __align__(16) float bbo[4];
     __align__(16) float slot[kSlots][kFields][kTile];
+    __align__(128) unsigned char av[kSmemAv ? kGroups : 1][kSmemAv ? kAvBytes : 128];   // v-tangent operands (5-tile map)
     __align__(128) unsigned char w16[128];    // hi+lo operand images of every layer: dynamic tail, hdr->f16_bytes long
 };
 static inline size_t tc_smem_bytes(int H, int n_hidden) {
@@ -470,7 +500,8 @@ __device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, 
 // 1..NH-1: hidden layer, NH: output layer (N = 16, fp32 accumulators throughout).
 // Order: u, z, v -- A_u is read first and D_v (which overlaps A_u) is written last.
 template <bool TANGENTS, int H>
-__device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint64_t b_first, uint64_t b_out, uint32_t bar) {
+__device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint64_t b_first, uint64_t b_out, uint64_t av_desc,
+                                            uint32_t bar) {
     constexpr uint32_t idz = make_idesc(H, true), idt = make_idesc(H, false), ido = make_idesc(16, true);
     // descriptor address units are 16 bytes.  One K chunk (16 halves = two core-matrix columns) of an [N x K] image
     // is 2 * N * 16 bytes; the LO image follows the HI image.
@@ -484,9 +515,9 @@ __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint6
         // layer images follow each other: bump the descriptor's 16-byte-granular address field (no carry: smem < 256 KB)
         const uint64_t b = (type == 0) ? b_first
                                        : b_first + (uint64_t)((kFirstBytes >> 4) + (uint32_t)(type - 1) * (kHidBytes >> 4));
-        const uint32_t a = tg + (type == 0 ? kColA1 : kColAh);
+        const uint32_t a = tg + col_ah<H>();
         const uint32_t lo = (type == 0) ? kLoFirst : kLoHid;
-        if (TANGENTS) {
+        if (TANGENTS && !kSmemAv) {
             mma_ts<0>(tg + kColDu, tg + kColAu, b, idt);
             if (type != 0) mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunk, idt);
         }
@@ -509,22 +540,33 @@ __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint6
                 for (int c = 2; c < H / 16; ++c) mma_ts<1>(tg + kColDz, a + 8 * c, b + lo + c * kChunk, idz);
             }
         }
-        if (TANGENTS) {
+        if (TANGENTS && kSmemAv) {                  // z has consumed A_h: D_u may now overwrite it
+            mma_ts<0>(tg + kColDu, tg + kColAu, b, idt);
+            if (type != 0) mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunk, idt);
+            mma_ss<0>(tg + kColDv, av_desc, b, idt);
+            if (type != 0) mma_ss<1>(tg + kColDv, av_desc + ((2u * 2048u) >> 4), b + kChunk, idt);
+        } else if (TANGENTS) {
             mma_ts<0>(tg + kColDv, tg + kColAv, b, idt);
             if (type != 0) mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + kChunk, idt);
         }
     } else {                                        // output layer, N = 16
         const uint64_t b = b_out;
-        if (TANGENTS) {
+        const uint32_t ah = tg + col_ah<H>();
+        if (TANGENTS && !kSmemAv) {
             mma_ts<0>(tg + kColDu, tg + kColAu, b, ido);
             mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunkOut, ido);
         }
-        mma_ts<0>(tg + kColDz, tg + kColAh, b, ido);
+        mma_ts<0>(tg + kColDz, ah, b, ido);
 #pragma unroll
-        for (int c = 1; c < H / 16; ++c) mma_ts<1>(tg + kColDz, tg + kColAh + 8 * c, b + c * kChunkOut, ido);
+        for (int c = 1; c < H / 16; ++c) mma_ts<1>(tg + kColDz, ah + 8 * c, b + c * kChunkOut, ido);
 #pragma unroll
-        for (int c = 0; c < H / 16; ++c) mma_ts<1>(tg + kColDz, tg + kColAh + 8 * c, b + kLoOut + c * kChunkOut, ido);
-        if (TANGENTS) {
+        for (int c = 0; c < H / 16; ++c) mma_ts<1>(tg + kColDz, ah + 8 * c, b + kLoOut + c * kChunkOut, ido);
+        if (TANGENTS && kSmemAv) {
+            mma_ts<0>(tg + kColDu, tg + kColAu, b, ido);
+            mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunkOut, ido);
+            mma_ss<0>(tg + kColDv, av_desc, b, ido);
+            mma_ss<1>(tg + kColDv, av_desc + ((2u * 2048u) >> 4), b + kChunkOut, ido);
+        } else if (TANGENTS) {
             mma_ts<0>(tg + kColDv, tg + kColAv, b, ido);
             mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + kChunkOut, ido);
         }
@@ -536,12 +578,13 @@ __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint6
 // before one elected lane issues the round.
 template <bool TANGENTS, int H>
 __device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH, uint32_t tg_mma, uint64_t b_hid0,
-                                                  uint64_t b_out, uint32_t bar) {
+                                                  uint64_t b_out, uint64_t av_desc, uint32_t bar) {
+    if (kSmemAv && TANGENTS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared operands -> tensor core
     tc_wait_st();
     tc_fence_before();
     group_sync(g);
     if (q == 0) {
-        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS, H>(type, NH, tg_mma, b_hid0, b_out, bar); }
+        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS, H>(type, NH, tg_mma, b_hid0, b_out, av_desc, bar); }
     }
 }
 
@@ -704,6 +747,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         const uint32_t w_base = smem_u32(S.w16);
         const uint64_t b_hid0 = make_b_desc(w_base, H * 16, 128);                // first / hidden layers: N = H rows
         uint64_t b_out = make_b_desc(w_base + 2u * H * 32u * 2u + (uint32_t)(NH - 1) * (2u * H * H * 2u), 256, 128);   // N = 16
+        uint64_t av_desc = kSmemAv ? make_b_desc(smem_u32(S.av[kSmemAv ? g : 0]), 2048, 128) : 0ull;   // A image: LBO 2048, SBO 128
+        const uint32_t av_row = smem_u32(S.av[kSmemAv ? g : 0]) + (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
         asm volatile("" : "+l"(b_out));                                         // keep it in registers (no per-round rebuild)
         uint32_t pd = 0;
         int sl = g;                                         // ring position / lap of this group's current tile
@@ -759,14 +804,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                         // weight image repeats W1[:,1], W1[:,2] there)
                         ev[0] = c23 << 16; ev[1] = (c01 >> 16) ^ 0x8000u; ev[2] = l23 << 16; ev[3] = (l01 >> 16) ^ 0x8000u;
                     }
-                    tmem_st8(tg + kColA1, a1);
-                    tmem_st8(tg + kColA1 + 8, a1 + 8);
+                    tmem_st8(tg + col_ah<H>(), a1);
+                    tmem_st8(tg + col_ah<H>() + 8, a1 + 8);
                     if (TANGENTS) {
                         tmem_st8(tg + kColAu, eu);
-                        tmem_st8(tg + kColAv, ev);
+                        if (kSmemAv) smem_st_a16(av_row, 0, ev); else tmem_st8(tg + kColAv, ev);
                     }
                 }
-                publish_and_issue<TANGENTS, H>(g, q, 0, NH, tg_mma, b_hid0, b_out, bar_d);
+                publish_and_issue<TANGENTS, H>(g, q, 0, NH, tg_mma, b_hid0, b_out, av_desc, bar_d);
 
                 // ---- activation rounds: layer 1 and the hidden layers share one instruction stream ----
 #pragma unroll 1
@@ -783,9 +828,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                             tc_wait_ld();
                             if (c + 1 < H / 16) tmem_ld16(tg + kColDz + 16 * (c + 1), zc[(c + 1) & 1]);
                             activate16<false, ACT>(zc[c & 1], nullptr, nullptr, ph, nullptr, nullptr);
-                            tmem_st8(tg + kColAh + 8 * c, ph);
+                            tmem_st8(tg + col_ah<H>() + 8 * c, ph);
                         }
-                        publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, bar_d);
+                        publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, av_desc, bar_d);
                         continue;
                     }
                     float za[16], zb[16];
@@ -797,13 +842,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                     if (TANGENTS) { tmem_ld8_pack16(tg + kColDu + 16, ub); tmem_ld8_pack16(tg + kColDv + 16, vb); }
                     uint32_t ph[8], pu[8], pv[8];
                     activate16<TANGENTS, ACT>(za, ua, va, ph, pu, pv);
-                    tmem_st8(tg + kColAh, ph);
-                    if (TANGENTS) { tmem_st8(tg + kColAu, pu); tmem_st8(tg + kColAv, pv); }
+                    tmem_st8(tg + col_ah<H>(), ph);
+                    if (TANGENTS) {
+                        tmem_st8(tg + kColAu, pu);
+                        if (kSmemAv) smem_st_a16(av_row, 0, pv); else tmem_st8(tg + kColAv, pv);
+                    }
                     tc_wait_ld();
                     activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
-                    tmem_st8(tg + kColAh + 8, ph);
-                    if (TANGENTS) { tmem_st8(tg + kColAu + 8, pu); tmem_st8(tg + kColAv + 8, pv); }
-                    publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, bar_d);
+                    tmem_st8(tg + col_ah<H>() + 8, ph);
+                    if (TANGENTS) {
+                        tmem_st8(tg + kColAu + 8, pu);
+                        if (kSmemAv) smem_st_a16(av_row, 2, pv); else tmem_st8(tg + kColAv + 8, pv);
+                    }
+                    publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, av_desc, bar_d);
                 }
 
                 // ---- output round: d, dd/dx0, dd/dx1 ----
