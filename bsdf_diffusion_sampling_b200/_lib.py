@@ -17,17 +17,18 @@ DISK, SPHERICAL = 0, 1
 EPI_RAW, EPI_DISK, EPI_SPHERICAL, EPI_BSDF = 0, 1, 2, 3
 PREC_FP32, PREC_TC16, PREC_TC16_EXP = 0, 1, 2
 BASE_FLOATS = 308
-ABI_VERSION = 1
+ABI_VERSION = 2
+OK_FP32_REROUTE = 1
 
 EXPORTS = [
     "bsdfdiff_abi_version", "bsdfdiff_error_string", "bsdfdiff_last_cuda_error", "bsdfdiff_debug_timeout_flag",
     "bsdfdiff_device_info",
-    "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn",
-    "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
+    "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_fixup_scratch_bytes",
+    "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_base_log_prob", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
 ]
 
 _c = ctypes
-_vp, _i, _i64, _u64 = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64
+_vp, _i, _i64, _u64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_float
 
 
 def _load() -> ctypes.CDLL:
@@ -45,13 +46,17 @@ def _load() -> ctypes.CDLL:
     lib.bsdfdiff_packed_flow_bytes.argtypes = [_i, _i, _i]
     lib.bsdfdiff_pack_flow.argtypes = [_c.POINTER(_vp), _c.POINTER(_i), _c.POINTER(_i), _i, _vp]
     lib.bsdfdiff_pack_flow_tcnn.argtypes = [_vp, _i, _i, _i, _i, _vp]
+    lib.bsdfdiff_fixup_scratch_bytes.restype = _c.c_size_t
+    lib.bsdfdiff_fixup_scratch_bytes.argtypes = [_i64]
     lib.bsdfdiff_sample.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _u64, _u64, _i64,
-                                    _vp, _vp, _vp, _vp]
-    lib.bsdfdiff_pdf.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]
+                                    _vp, _vp, _vp, _f, _vp, _vp]
+    lib.bsdfdiff_pdf.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _vp]
+    lib.bsdfdiff_base_log_prob.argtypes = [_i, _i64, _vp, _vp, _vp, _vp, _vp]
     lib.bsdfdiff_flow_forward.argtypes = [_i, _i, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _u64, _u64, _i64,
                                           _vp, _vp, _vp]
     lib.bsdfdiff_mlp_forward.argtypes = [_i, _i64, _vp, _i, _vp, _i, _i, _vp, _vp]
     for name in ("bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_sample", "bsdfdiff_pdf",
+                 "bsdfdiff_base_log_prob",
                  "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward", "bsdfdiff_device_info"):
         getattr(lib, name).restype = _i
     if lib.bsdfdiff_abi_version() != ABI_VERSION:
@@ -66,7 +71,18 @@ class BsdfDiffError(RuntimeError):
     pass
 
 
+# number of calls the library answered with BSDFDIFF_OK_FP32_REROUTE (a tensor-core request whose net shape only the
+# fp32 CUDA-core kernel covers); BSDFDIFF_STRICT_TC=1 turns the reroute into an error
+fp32_reroutes = 0
+
+
 def check(rc: int, what: str) -> None:
+    global fp32_reroutes
+    if rc == OK_FP32_REROUTE:
+        fp32_reroutes += 1
+        if os.environ.get("BSDFDIFF_STRICT_TC") == "1":
+            raise BsdfDiffError(f"{what}: {lib.bsdfdiff_error_string(rc).decode()} (BSDFDIFF_STRICT_TC=1)")
+        return
     if rc != 0:
         msg = lib.bsdfdiff_error_string(rc).decode()
         extra = f" (cudaError {lib.bsdfdiff_last_cuda_error()})" if rc == -3 else ""

@@ -20,6 +20,7 @@ extern "C" int bsdfdiff_abi_version(void) { return BSDFDIFF_ABI_VERSION; }
 extern "C" const char* bsdfdiff_error_string(int code) {
     switch (code) {
         case BSDFDIFF_OK: return "ok";
+        case BSDFDIFF_OK_FP32_REROUTE: return "ok (shape not covered by the tensor-core kernel: ran on the fp32 CUDA-core kernel)";
         case BSDFDIFF_EINVAL: return "invalid argument";
         case BSDFDIFF_EUNSUPPORTED: return "shape not supported by the requested precision path";
         case BSDFDIFF_ECUDA: return "CUDA runtime error";
@@ -50,14 +51,11 @@ extern "C" int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor)
 // ------------------------------------------------------------------------------------------------
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static size_t aux_floats(int H) { return 3 * (size_t)H; }
-
 extern "C" size_t bsdfdiff_packed_flow_bytes(int in_dim, int hidden, int n_hidden) {
     if (in_dim < 1 || in_dim > 32 || (hidden != 32 && hidden != 64) || n_hidden < 1 || n_hidden > 16) return 0;
     size_t b = sizeof(PackedHeader);
     b += align_up(sizeof(float) * f32_image_floats(in_dim, hidden, n_hidden), 128);
     b += align_up(sizeof(__half) * f16_image_halves(hidden, n_hidden), 128);
-    b += align_up(sizeof(float) * aux_floats(hidden), 128);
     return b;
 }
 
@@ -112,8 +110,6 @@ static int pack_from_layers(const std::vector<const float*>& Ws, const std::vect
     hdr.f32_bytes = (uint32_t)(sizeof(float) * f32_image_floats(in_dim, H, n_hidden));
     hdr.off_f16 = hdr.off_f32 + (uint32_t)align_up(hdr.f32_bytes, 128);
     hdr.f16_bytes = (uint32_t)(sizeof(__half) * f16_image_halves(H, n_hidden));
-    hdr.reserved[0] = hdr.off_f16 + (uint32_t)align_up(hdr.f16_bytes, 128);   // aux offset
-    hdr.reserved[1] = (uint32_t)(sizeof(float) * aux_floats(H));
     hdr.total_bytes = (uint32_t)total;
     std::memcpy(out, &hdr, sizeof(hdr));
 
@@ -150,12 +146,6 @@ static int pack_from_layers(const std::vector<const float*>& Ws, const std::vect
         for (int k = 0; k < H; ++k)
             put(h, (size_t)16 * H, n, k, 16, (n < 2) ? Ws[n_layers - 1][(size_t)n * H + k] : 0.0f);
 
-    // aux: 0.5 * W1[:,0], 0.5 * W1[:,1], 0.5 * W1[:,2]  (first-layer tangent seeds, fp16-rounded like
-    // the operand image so value and tangent paths see the same weights)
-    float* aux = reinterpret_cast<float*>(out + hdr.reserved[0]);
-    for (int c = 0; c < 3; ++c)
-        for (int j = 0; j < H; ++j)
-            aux[c * H + j] = (c < in_dim) ? __half2float(__float2half_rn(0.5f * Ws[0][(size_t)j * in_dim + c])) : 0.0f;
     return BSDFDIFF_OK;
 }
 
@@ -202,14 +192,44 @@ static int dispatch(int precision, const FlowParams& P, cudaStream_t stream) {
     if (precision == BSDFDIFF_PREC_FP32 || P.T == 0) rc = launch_simt(P, stream);
     else if (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP) {
         rc = launch_tc(P, stream, precision);
-        // shapes the tcgen05 kernel does not cover yet (64-wide reflow teacher nets) run on the CUDA-core
-        // kernel of the same library -- still a GPU path, never a CPU fallback
-        if (rc == -2) rc = launch_simt(P, stream);
+        // shapes the tcgen05 kernel does not cover (more than 6 hidden layers; sample/pdf with a 64-wide net -- none of
+        // which the reference instantiates) run on the CUDA-core kernel of the same library: still a GPU path, never a
+        // CPU fallback, and the caller is TOLD: the call returns BSDFDIFF_OK_FP32_REROUTE (> 0) instead of 0
+        if (rc == -2) {
+            FlowParams Q = P;
+            Q.fix_thr = 0.0f; Q.fix_count = nullptr; Q.fix_list = nullptr;
+            rc = launch_simt(Q, stream);
+            if (rc == 0) return BSDFDIFF_OK_FP32_REROUTE;
+        }
     }
     else return BSDFDIFF_EINVAL;
     if (rc == -3) return fail_cuda();
+    if (rc == -4) return BSDFDIFF_ENOTSM100;
     return rc;
 }
+
+// PREC_TC16 with the conditioning-triggered fp32 fix-up: [memset count] -> tensor-core kernel (flags rows) -> CUDA-core
+// kernel over the flagged rows.  scratch = [count u32, pad to 16 B][row list u32 x n].
+static int dispatch_fixup(int precision, FlowParams P, cudaStream_t stream, float thr, void* scratch) {
+    const bool tc = (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP);
+    if (!(thr > 0.0f) || !tc || P.T == 0) return dispatch(precision, P, stream);
+    if (!scratch || P.n > 0xffffffffll) return BSDFDIFF_EINVAL;
+    if (P.mode == kModeSample && !P.x0 && !P.out_x0) return BSDFDIFF_EINVAL;   // the fix-up pass replays the base sample
+    P.fix_thr = thr;
+    P.fix_count = static_cast<unsigned int*>(scratch);
+    P.fix_list = P.fix_count + 4;
+    if (cudaMemsetAsync(P.fix_count, 0, 16, stream) != cudaSuccess) return fail_cuda();
+    int rc = dispatch(precision, P, stream);
+    if (rc != BSDFDIFF_OK) return rc;               // errors, and the fp32 reroute (nothing left to fix)
+    FlowParams Q = P;
+    Q.fix_pass = 1;
+    if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; }
+    rc = launch_simt(Q, stream);
+    if (rc == -3) return fail_cuda();
+    return rc;
+}
+
+extern "C" size_t bsdfdiff_fixup_scratch_bytes(int64_t n) { return n < 0 ? 0 : 16 + sizeof(unsigned int) * (size_t)n; }
 
 static int fill_shape(FlowParams& P, const void* flow_packed, int domain, int hidden, int n_hidden) {
     if ((hidden != 32 && hidden != 64) || n_hidden < 1 || n_hidden > 16) return BSDFDIFF_EUNSUPPORTED;
@@ -221,7 +241,8 @@ static int fill_shape(FlowParams& P, const void* flow_packed, int domain, int hi
 extern "C" int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
                                const float* wi, const void* flow_packed, int hidden, int n_hidden,
                                const float* base_params, const float* x0_replay, uint64_t seed, uint64_t offset, int64_t first_index,
-                               float* out_dir, float* out_pdf, float* out_x0, void* cuda_stream) {
+                               float* out_dir, float* out_pdf, float* out_x0, float fix_threshold, void* fix_scratch,
+                               void* cuda_stream) {
     // T == 0 with flow_packed == NULL evaluates the base distribution alone (D_base.sample / log_prob)
     if (n < 0 || T < 0 || ((T == 0) != (flow_packed == nullptr)) || !base_params ||
         (domain != kDisk && domain != kSpherical) ||
@@ -237,12 +258,13 @@ extern "C" int bsdfdiff_sample(int precision, int domain, int epilogue, int T, i
     P.out_dir = out_dir; P.out_pdf = out_pdf; P.out_x0 = out_x0;
     int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
     if (rc) return rc;
-    return dispatch(precision, P, stream);
+    return dispatch_fixup(precision, P, stream, fix_threshold, fix_scratch);
 }
 
 extern "C" int bsdfdiff_pdf(int precision, int domain, int epilogue, int T, int64_t n,
                             const float* wo, const float* wi, const void* flow_packed, int hidden, int n_hidden,
-                            const float* base_params, float* out_pdf, void* cuda_stream) {
+                            const float* base_params, float* out_pdf, float fix_threshold, void* fix_scratch,
+                            void* cuda_stream) {
     if (n < 0 || T < 0 || ((T == 0) != (flow_packed == nullptr)) || !base_params ||
         (domain != kDisk && domain != kSpherical) ||
         epilogue < 0 || epilogue > 3 || (epilogue == kEpiDisk && domain != kDisk) ||
@@ -256,7 +278,21 @@ extern "C" int bsdfdiff_pdf(int precision, int domain, int epilogue, int T, int6
     P.wi = wi; P.wo = wo; P.base = base_params; P.out_pdf = out_pdf;
     int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
     if (rc) return rc;
-    return dispatch(precision, P, stream);
+    return dispatch_fixup(precision, P, stream, fix_threshold, fix_scratch);
+}
+
+extern "C" int bsdfdiff_base_log_prob(int domain, int64_t n, const float* x, const float* wi, const float* base_params,
+                                      float* out_logp, void* cuda_stream) {
+    if (n < 0 || !base_params || (domain != kDisk && domain != kSpherical)) return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    if (!x || !wi || !out_logp) return BSDFDIFF_EINVAL;
+    FlowParams P{};
+    P.domain = domain; P.mode = kModePdf; P.epilogue = kEpiRaw; P.T = 0; P.n = n; P.wi_repeat = 1;
+    P.wi = wi; P.wo = x; P.base = base_params; P.out_pdf = out_logp; P.log_output = 1;
+    P.in_dim = (domain == kDisk) ? 25 : 26; P.hidden = 32; P.n_hidden = 1;
+    int rc = launch_simt(P, static_cast<cudaStream_t>(cuda_stream));
+    if (rc == -3) return fail_cuda();
+    return rc;
 }
 
 extern "C" int bsdfdiff_flow_forward(int precision, int domain, int T, int64_t n, const float* wi, int64_t wi_repeat,

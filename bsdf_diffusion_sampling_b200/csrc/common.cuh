@@ -73,7 +73,47 @@ struct FlowParams {
     float* out_dir;               // [n,2] or [n,3]
     float* out_pdf;               // [n]
     float* out_x0;                // optional [n,2]
+    // conditioning-triggered fp32 fix-up (PREC_TC16 only): the tensor-core kernel appends the row index of
+    // every query whose pdf is ill-conditioned w.r.t. fp16 rounding (weight < fix_thr, see cond_weight()) to
+    // fix_list[atomicAdd(fix_count)]; the CUDA-core kernel then recomputes exactly those rows in fp32
+    float fix_thr;                // 0 = off
+    unsigned int* fix_count;      // device counter (zeroed by the caller before the tensor-core launch)
+    unsigned int* fix_list;       // device list, capacity n
+    int fix_pass;                 // 1: this launch IS the fix-up pass (flow_simt_kernel walks fix_list)
+    int log_output;               // pdf mode, T == 0, raw epilogue: store log p_base instead of p_base (D_base.log_prob)
 };
+
+// Conditioning weight in (0,1] of a query's pdf w.r.t. rounding inside the flow -- the same three factors the
+// oracle reports (oracle/bsdf_oracle.c euler(), bsdf_oracle_pdf()):  pdf = p0 (/|*) prod det_t, so an absolute error
+// in a step determinant is a relative pdf error ~ 1/|det_t| (factor min(1, min|det| / 0.2)); a state error made early
+// is amplified by the later steps' Jacobians (factor min(1, 16 / prod max(1, sigma_max(J_t)))); pdf() evaluates the
+// base density at the END of the reverse flow (factor min(1, 25 / |grad log p_base|)).
+struct CondTrack {
+    float mind, ampsq;            // min_t |det_t|, prod_t max(1, sigma_max(J_t)^2)
+    __device__ __forceinline__ void reset() { mind = FLT_MAX; ampsq = 1.0f; }
+    __device__ __forceinline__ void step(float j00, float j01, float j10, float j11, float det) {
+        mind = fminf(mind, fabsf(det));
+        const float fro = j00 * j00 + j01 * j01 + j10 * j10 + j11 * j11;
+        const float s2max = 0.5f * (fro + sqrtf(fmaxf(fro * fro - 4.0f * det * det, 0.0f)));
+        ampsq *= fmaxf(1.0f, s2max);
+    }
+    __device__ __forceinline__ float weight() const {
+        return fminf(1.0f, mind * 5.0f) * fminf(1.0f, 16.0f * rsqrtf(ampsq));
+    }
+};
+// |grad_x log p_base(x)| (model.py:393-398 disk, :308-317 spherical)
+__device__ __forceinline__ float base_grad_norm(int domain, const float p[4], float kappa, float x0, float x1) {
+    float g0, g1;
+    if (domain == kDisk) {
+        g0 = (x0 - p[0]) * __expf(-2.0f * p[2]);
+        g1 = (x1 - p[1]) * __expf(-2.0f * p[3]);
+    } else {
+        const float sc = __expf(p[1]) + 1e-3f;
+        g0 = (x0 - p[0]) / (sc * sc);
+        g1 = kappa * __sinf(x1 - p[2]);
+    }
+    return sqrtf(g0 * g0 + g1 * g1);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011), counter = (index lo, index hi, offset lo + round, offset hi)

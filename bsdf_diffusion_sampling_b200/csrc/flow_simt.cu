@@ -123,6 +123,13 @@ __device__ __forceinline__ void velocity(const float* __restrict__ W, int domain
 template <int H, bool TANGENTS>
 __global__ void __launch_bounds__(kThreads) flow_simt_kernel(const FlowParams P) {
     extern __shared__ __align__(16) float smem[];
+    // fix-up pass: the rows to recompute are fix_list[0 .. *fix_count) (written by the tensor-core kernel that ran
+    // before this launch on the same stream); most launches find an empty or tiny list and leave before staging weights
+    long long n_rows = P.n;
+    if (P.fix_pass) {
+        n_rows = (long long)min(*P.fix_count, (unsigned int)min(P.n, (long long)0xffffffffll));
+        if ((long long)blockIdx.x * kThreads >= n_rows) return;
+    }
     const int n_w = P.flow ? f32_image_floats(P.in_dim, H, P.n_hidden) : 0;     // T == 0: base net only
     float* W = smem;
     float* base = W + ((n_w + 3) & ~3);
@@ -140,8 +147,9 @@ __global__ void __launch_bounds__(kThreads) flow_simt_kernel(const FlowParams P)
     const int k0 = (P.domain == kDisk) ? 3 : 4;      // first PE column of layer 1
     const float inv_t = (float)(1.0 / (double)P.T);
 
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < P.n;
-         i += (long long)gridDim.x * kThreads) {
+    for (long long jj = (long long)blockIdx.x * kThreads + threadIdx.x; jj < n_rows;
+         jj += (long long)gridDim.x * kThreads) {
+        const long long i = P.fix_pass ? (long long)P.fix_list[jj] : jj;
         float w0, w1, wiz;
         load_wi(P, i, w0, w1, wiz);
 
@@ -199,7 +207,9 @@ __global__ void __launch_bounds__(kThreads) flow_simt_kernel(const FlowParams P)
             store_sample(P, i, x0, x1, p0 * R);
         } else if (P.mode == kModePdf) {
             base_eval(base, w0, w1, bp);
-            store_pdf(P, i, expf(base_logprob(P.domain, bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
+            const float lp = base_logprob(P.domain, bp, x0, x1);
+            if (P.log_output) P.out_pdf[i] = lp;            // model.py:393-398 / 308-317 return the LOG density
+            else store_pdf(P, i, expf(lp) * R, wiz, wox, woy, woz, theta_o);
         } else {
             reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
         }
@@ -221,6 +231,7 @@ static int launch_simt_t(const FlowParams& P, cudaStream_t stream) {
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
     if (grid < 1) return 0;
+    if (P.fix_pass && (!P.fix_count || !P.fix_list)) return -1;
     kern<<<(unsigned)grid, kThreads, smem, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

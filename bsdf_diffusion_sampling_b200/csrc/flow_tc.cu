@@ -440,6 +440,18 @@ __device__ __forceinline__ void base_draw_fast(const float p[4], unsigned long l
     x1 = y - 3.14159265358979f;
 }
 
+// Append row i to the fix-up list (warp-aggregated: one atomic per warp that has any flagged row).  Called by all 32
+// lanes of a converged worker warp.
+__device__ __forceinline__ void flag_for_fixup(const FlowParams& P, bool flag, long long i) {
+    const uint32_t mask = __ballot_sync(0xffffffffu, flag);
+    if (mask == 0u) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.fix_count, (unsigned int)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (flag) P.fix_list[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned int)i;
+}
+
 struct TcSmem {
     unsigned long long d_ready[kGroups];
     unsigned long long w_bar;
@@ -765,6 +777,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
             // ---- take this row's record from the producer ----
             float x0, x1, R = 1.0f, p0 = 1.0f;
+            CondTrack cond;
+            cond.reset();
             mbar_wait(smem_u32(&S.full[sl]), use & 1u);
             const float (*f)[kTile] = S.slot[sl];
             x0 = f[kFX][row]; x1 = f[kFX + 1][row];
@@ -869,6 +883,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                     const float j10 = step * du1, j11 = fmaf(step, dv1, 1.0f);
                     const float det = j00 * j11 - j01 * j10;
                     R = (MODE == kModePdf) ? R * det : __fdividef(R, det);
+                    cond.step(j00, j01, j10, j11, det);
                 }
                 x0 = fmaf(step, d0, x0);
                 x1 = fmaf(step, d1, x1);
@@ -876,6 +891,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
             if (MODE == kModeSample) {
                 if (valid) store_sample<true>(P, i, x0, x1, p0 * R);
+                if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && cond.weight() < P.fix_thr, i);
             } else if (MODE == kModePdf) {
                 float bp[4];
 #pragma unroll
@@ -885,6 +901,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
                 if (valid)
                     store_pdf<true>(P, i, __expf(base_logprob_fast<DOMAIN>(bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
+                if (P.fix_thr > 0.0f) {
+                    const float kappa = (DOMAIN == kDisk) ? 0.0f : softplus_fast(bp[3]) + 1e-3f;
+                    const float gn = base_grad_norm(DOMAIN, bp, kappa, x0, x1);
+                    flag_for_fixup(P, valid && cond.weight() * fminf(1.0f, __fdividef(25.0f, gn)) < P.fix_thr, i);
+                }
             } else {
                 if (valid) reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
             }
@@ -914,12 +935,10 @@ static int launch_tc_t(const FlowParams& P, cudaStream_t stream) {
     if (grid < 1) return 0;
     const size_t smem = tc_smem_bytes(H, P.n_hidden);
     if (smem > 227u * 1024u) return -2;
-    static size_t attr_bytes = 0;            // per instantiation; benign if two host threads race (monotone)
-    if (smem > attr_bytes) {
-        if (cudaFuncSetAttribute(flow_tc_kernel<DOMAIN, MODE, ACT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem) != cudaSuccess) return -3;
-        attr_bytes = smem;
-    }
+    // the opt-in is per DEVICE (a process may drive several GPUs): set it on every launch, like launch_simt_t does --
+    // cheap and CUDA-graph-capture safe
+    if (cudaFuncSetAttribute(flow_tc_kernel<DOMAIN, MODE, ACT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess) return -3;
     flow_tc_kernel<DOMAIN, MODE, ACT, H><<<(unsigned)grid, kTcThreads, smem, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
@@ -939,6 +958,12 @@ static int launch_tc_m(const FlowParams& P, cudaStream_t stream) {
 
 // variant 1 = tc16 (tanh.approx activation), 2 = tc16 with fp32 exp-form activation (cross-check)
 int launch_tc(const FlowParams& P, cudaStream_t stream, int variant) {
+    {   // tcgen05 / TMEM exist on compute capability 10.x only
+        int dev = 0, major = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -3;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        if (major != 10) return -4;
+    }
     if ((P.hidden != 32 && P.hidden != 64) || P.n_hidden < 2 || P.n_hidden > 6) return -2;   // else: CUDA-core path
     if (P.domain == kDisk)
         return variant == 2 ? launch_tc_m<kDisk, 0>(P, stream) : launch_tc_m<kDisk, 1>(P, stream);

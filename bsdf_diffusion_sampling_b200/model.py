@@ -5,6 +5,10 @@ Only the six symbols that are live on the reference's hot path are provided (SUR
 rendering/utils/model.py:479-501), ``NN_cond_pos`` (:422-446), ``NN_cond_pos_spherical_complicate``
 (:449-477), ``NN_cond_pretrain_disk_one`` (:374-398) and ``NN_cond_pretrain_spherical_one`` (:277-317).
 
+INFERENCE ONLY: ``forward`` / ``sample`` / ``log_prob`` are detached CUDA-library calls with no autograd, so the
+reference's TRAINING stages (losses on ``log_prob`` / ``forward``) cannot backpropagate through them -- they raise
+instead of silently returning constants when gradients are expected (call them under ``torch.no_grad()``).
+
 These modules are *parameter containers*: their ``state_dict`` keys (``linear{k}.weight``,
 ``output.weight`` [+ ``.bias`` for the base nets]) match the reference so its checkpoints load
 unchanged, and the samplers in ``mlp_brdf_sampling`` pack them for the CUDA kernels.  ``forward``,
@@ -35,6 +39,14 @@ def positional_encoding_1(tensor: torch.Tensor, num_encoding_functions: int = 6,
     return parts[0] if len(parts) == 1 else torch.cat(parts, dim=-1)
 
 
+def _inference_only(module: nn.Module, what: str, *tensors) -> None:
+    if torch.is_grad_enabled() and (any(p.requires_grad for p in module.parameters())
+                                    or any(t.requires_grad for t in tensors)):
+        raise RuntimeError(
+            f"{type(module).__name__}.{what}: this drop-in is inference-only (a detached CUDA-library call, no "
+            "autograd); wrap the call in torch.no_grad(), or train with the reference's own nn.Module")
+
+
 class _FlowNet(nn.Module):
     """Bias-free SiLU MLP  input_dim + 4*PE  ->  H  -> ... -> output_dim."""
     N_HIDDEN = 0
@@ -50,6 +62,7 @@ class _FlowNet(nn.Module):
 
     def forward(self, x, alpha, x_co):
         """Velocity D(x, alpha | x_co): one fused MLP forward on the GPU."""
+        _inference_only(self, "forward", x, x_co)
         packed = weights.packed_flow_of(self, x.device)
         inp = torch.cat([x, alpha, positional_encoding_1(x_co, self.pos_num)], dim=1)
         return ops.mlp_forward(inp, packed)
@@ -106,15 +119,17 @@ class NN_cond_pretrain_spherical_one(_BaseNet):
 
 def _base_sample(self, x_co, numsamples=1):
     """x0 ~ p_base(. | x_co), drawn on the GPU with Philox (T = 0 call of the fused sampler)."""
+    _inference_only(self, "sample", x_co)
     base = weights.packed_base_of(self, x_co.device)
     x0, _, _ = ops.sample(x_co, ops.NullFlow(self.DOMAIN), base, 0)
     return x0
 
 
 def _base_log_prob(self, x, x_co):
-    """log p_base(x | x_co) (T = 0 call of the fused pdf kernel)."""
+    """log p_base(x | x_co): the kernel returns the log density itself (finite where the density underflows)."""
+    _inference_only(self, "log_prob", x, x_co)
     base = weights.packed_base_of(self, x_co.device)
-    return torch.log(ops.pdf(x, x_co, ops.NullFlow(self.DOMAIN), base, 0))
+    return ops.base_log_prob(x, x_co, base, self.DOMAIN)
 
 
 _BaseNet.sample = _base_sample

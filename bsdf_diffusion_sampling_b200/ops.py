@@ -60,11 +60,50 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
 
 def next_philox(device) -> Tuple[int, int]:
     """(seed, offset) from torch's CUDA generator, advancing it -- ``torch.manual_seed`` keeps
-    controlling the sampler, like the reference's ``torch.randn_like`` (rendering/utils/model.py:390)."""
+    controlling the sampler, like the reference's ``torch.randn_like`` (rendering/utils/model.py:390).
+
+    The pair is read on the host and handed to the kernel BY VALUE, so it must not be baked into a CUDA graph
+    (every replay would return the same base samples, where torch's own ``randn`` advances a device-side
+    offset): under stream capture this raises; capture with an explicit ``seed=``/``offset=`` or a replayed
+    ``x0=`` instead."""
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError("bsdfdiff: drawing (seed, offset) from torch's generator is not CUDA-graph capturable; "
+                           "pass seed=/offset= (or x0=) explicitly when capturing")
     gen = torch.cuda.default_generators[torch.device(device).index or 0]
     seed, offset = gen.initial_seed(), gen.get_offset()
     gen.set_offset(offset + PHILOX_OFFSET_PER_CALL)
     return seed & (2 ** 63 - 1), offset
+
+
+# ---- conditioning-triggered fp32 fix-up of the tc16 path (include/bsdfdiff.h) ---------------------------------
+_fixup_threshold = float(os.environ.get("BSDFDIFF_FIXUP", "0.25"))
+_last_fix_scratch = {}
+
+
+def set_fixup_threshold(thr: float) -> None:
+    """Conditioning weight below which a tc16 query is recomputed in fp32 (0 disables the second launch)."""
+    global _fixup_threshold
+    _fixup_threshold = float(thr)
+
+
+def get_fixup_threshold() -> float:
+    return _fixup_threshold
+
+
+def last_fixup_count(device=None) -> int:
+    """Rows the most recent tc16 call on ``device`` recomputed in fp32 (synchronises; diagnostics only)."""
+    dev = torch.device(device if device is not None else "cuda")
+    t = _last_fix_scratch.get(dev.index or 0)
+    return int(t[0].item()) if t is not None else 0
+
+
+def _fix_scratch(n: int, device: torch.device, precision: int, fix_thr: float, T: int) -> Optional[torch.Tensor]:
+    if not (fix_thr > 0.0) or precision == PREC_FP32 or T == 0:
+        return None
+    t = torch.empty((_lib.lib.bsdfdiff_fixup_scratch_bytes(n) + 3) // 4, dtype=torch.int32, device=device)
+    if not torch.cuda.is_current_stream_capturing():
+        _last_fix_scratch[device.index or 0] = t
+    return t
 
 
 # ------------------------------------------------------------------------------------------------
@@ -74,60 +113,88 @@ def next_philox(device) -> Tuple[int, int]:
 def _sample_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor, x0: Optional[torch.Tensor],
                precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
                seed: int, offset: int, first_index: int,
-               want_x0: bool) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+               want_x0: bool, fix_thr: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     n = wi.shape[0]
     out_dir = torch.empty((n, 2 if epilogue == EPI_RAW else 3), dtype=torch.float32, device=wi.device)
     out_pdf = torch.empty((n,), dtype=torch.float32, device=wi.device)
-    out_x0 = torch.empty((n if want_x0 else 0, 2), dtype=torch.float32, device=wi.device)
+    scratch = _fix_scratch(n, wi.device, precision, fix_thr, T)
+    need_x0 = want_x0 or (scratch is not None and x0 is None)      # the fix-up pass replays the base sample
+    out_x0 = torch.empty((n if need_x0 else 0, 2), dtype=torch.float32, device=wi.device)
     with torch.cuda.device(wi.device):
         rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
                                       flow_blob.data_ptr() if flow_blob is not None else None,
                                       hidden, n_hidden, base.data_ptr(), x0.data_ptr() if x0 is not None else None,
                                       seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(),
-                                      out_x0.data_ptr() if want_x0 else None, _stream(wi))
+                                      out_x0.data_ptr() if need_x0 else None,
+                                      fix_thr if scratch is not None else 0.0,
+                                      scratch.data_ptr() if scratch is not None else None, _stream(wi))
     _lib.check(rc, "bsdfdiff_sample")
-    return out_dir, out_pdf, out_x0
+    return out_dir, out_pdf, (out_x0 if want_x0 else out_x0[:0])
 
 
 @_sample_op.register_fake
-def _(wi, flow_blob, base, x0, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, want_x0):
+def _(wi, flow_blob, base, x0, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, want_x0,
+      fix_thr):
     n = wi.shape[0]
     return (wi.new_empty((n, 2 if epilogue == EPI_RAW else 3)), wi.new_empty((n,)),
             wi.new_empty((n if want_x0 else 0, 2)))
 
 
-@torch.library.custom_op("bsdfdiff::sample_out", mutates_args=("out_dir", "out_pdf"), device_types="cuda")
+@torch.library.custom_op("bsdfdiff::sample_out", mutates_args=("out_dir", "out_pdf", "scratch"), device_types="cuda")
 def _sample_out_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor, x0: Optional[torch.Tensor],
-                   out_dir: torch.Tensor, out_pdf: torch.Tensor,
+                   out_dir: torch.Tensor, out_pdf: torch.Tensor, scratch: Optional[torch.Tensor],
                    precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
-                   seed: int, offset: int, first_index: int) -> None:
-    """As ``bsdfdiff::sample`` but writes into caller-owned buffers (no allocation: streaming pipelines)."""
+                   seed: int, offset: int, first_index: int, fix_thr: float) -> None:
+    """As ``bsdfdiff::sample`` but writes into caller-owned buffers (no allocation: streaming pipelines).
+    ``scratch`` (int32, >= 4 + 3 n elements) enables the fix-up: [count, pad x3][row list n][base sample 2 n]."""
     n = wi.shape[0]
+    fix = scratch is not None and fix_thr > 0.0 and precision != PREC_FP32 and T > 0
+    x0_side = None
+    if fix and x0 is None:
+        x0_side = scratch[4 + n:4 + 3 * n].view(torch.float32)
     with torch.cuda.device(wi.device):
         rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
                                       flow_blob.data_ptr() if flow_blob is not None else None,
                                       hidden, n_hidden, base.data_ptr(), x0.data_ptr() if x0 is not None else None,
-                                      seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(), None,
-                                      _stream(wi))
+                                      seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(),
+                                      x0_side.data_ptr() if x0_side is not None else None,
+                                      fix_thr if fix else 0.0, scratch.data_ptr() if fix else None, _stream(wi))
     _lib.check(rc, "bsdfdiff_sample")
 
 
 @torch.library.custom_op("bsdfdiff::pdf", mutates_args=(), device_types="cuda")
 def _pdf_op(wo: torch.Tensor, wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor,
-            precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int) -> torch.Tensor:
+            precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
+            fix_thr: float) -> torch.Tensor:
     n = wi.shape[0]
     out = torch.empty((n,), dtype=torch.float32, device=wi.device)
+    scratch = _fix_scratch(n, wi.device, precision, fix_thr, T)
     with torch.cuda.device(wi.device):
         rc = _lib.lib.bsdfdiff_pdf(precision, domain, epilogue, T, n, wo.data_ptr(), wi.data_ptr(),
                                    flow_blob.data_ptr() if flow_blob is not None else None, hidden, n_hidden,
-                                   base.data_ptr(), out.data_ptr(),
-                                   _stream(wi))
+                                   base.data_ptr(), out.data_ptr(), fix_thr if scratch is not None else 0.0,
+                                   scratch.data_ptr() if scratch is not None else None, _stream(wi))
     _lib.check(rc, "bsdfdiff_pdf")
     return out
 
 
 @_pdf_op.register_fake
-def _(wo, wi, flow_blob, base, precision, domain, epilogue, T, hidden, n_hidden):
+def _(wo, wi, flow_blob, base, precision, domain, epilogue, T, hidden, n_hidden, fix_thr):
+    return wi.new_empty((wi.shape[0],))
+
+
+@torch.library.custom_op("bsdfdiff::base_log_prob", mutates_args=(), device_types="cuda")
+def _base_log_prob_op(x: torch.Tensor, wi: torch.Tensor, base: torch.Tensor, domain: int) -> torch.Tensor:
+    out = torch.empty((wi.shape[0],), dtype=torch.float32, device=wi.device)
+    with torch.cuda.device(wi.device):
+        rc = _lib.lib.bsdfdiff_base_log_prob(domain, wi.shape[0], x.data_ptr(), wi.data_ptr(), base.data_ptr(),
+                                             out.data_ptr(), _stream(wi))
+    _lib.check(rc, "bsdfdiff_base_log_prob")
+    return out
+
+
+@_base_log_prob_op.register_fake
+def _(x, wi, base, domain):
     return wi.new_empty((wi.shape[0],))
 
 
@@ -181,56 +248,98 @@ class NullFlow:
         self.in_dim = 25 if domain == DISK else 26
 
 
-def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,
-           x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0, first_index: int = 0,
-           precision=None, return_x0: bool = True):
-    """-> (dir [n,2|3], pdf [n], x0 [n,2]).  ``flow`` is a ``weights.PackedFlow``.
-    ``return_x0=False`` skips materialising the base sample (8 B/query of HBM writes); x0 is then empty."""
-    _require_cuda(wi, "sample")
-    wi = _f32c(wi)
+def _check_flow(flow, T: int, what: str) -> None:
     if T < 0 or (T == 0) != (flow.blob is None):
         raise ValueError("T must be >= 1 (T == 0 only with NullFlow: base distribution alone)")
+    if flow.in_dim not in (25, 26):
+        raise ValueError(f"bsdfdiff.{what}: the sampler nets take 25 (disk) or 26 (spherical) inputs, got {flow.in_dim}")
+
+
+def _check_rows(t: torch.Tensor, n: int, cols: int, what: str) -> None:
+    if t.dim() != 2 or t.shape[0] != n or t.shape[1] != cols:
+        raise ValueError(f"bsdfdiff: {what} must have shape ({n}, {cols}), got {tuple(t.shape)}")
+
+
+def _fix_thr(fixup) -> float:
+    return _fixup_threshold if fixup is None else float(fixup)
+
+
+def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,
+           x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0, first_index: int = 0,
+           precision=None, return_x0: bool = True, fixup=None):
+    """-> (dir [n,2|3], pdf [n], x0 [n,2]).  ``flow`` is a ``weights.PackedFlow``.
+    ``return_x0=False`` skips returning the base sample; x0 is then empty.  ``fixup`` = conditioning threshold of the
+    fp32 fix-up pass of the tc16 path (None: the module default, 0: off)."""
+    _require_cuda(wi, "sample")
+    wi = _f32c(wi)
+    _check_flow(flow, T, "sample")
+    _check_rows(wi, wi.shape[0], 2 if epilogue == EPI_RAW else 3, "wi")
     if x0 is not None:
         x0 = _f32c(x0, wi.device)
+        _check_rows(x0, wi.shape[0], 2, "x0")
         seed, offset = 0, 0
     elif seed is None:
         seed, offset = next_philox(wi.device)
     return _sample_op(wi, flow.blob, base, x0, _resolve_precision(precision), flow.domain, epilogue, int(T),
-                      flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), bool(return_x0))
+                      flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), bool(return_x0),
+                      _fix_thr(fixup))
+
+
+def sample_scratch_elems(n: int) -> int:
+    """int32 elements of the scratch buffer ``sample_into`` needs for ``n`` rows when the fix-up is on."""
+    return 4 + 3 * int(n)
 
 
 def sample_into(wi: torch.Tensor, flow, base: torch.Tensor, T: int, out_dir: torch.Tensor, out_pdf: torch.Tensor, *,
                 epilogue: int = EPI_RAW, x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0,
-                first_index: int = 0, precision=None) -> None:
-    """``sample`` into caller-owned contiguous fp32 CUDA buffers ``out_dir`` [n,2|3] and ``out_pdf`` [n]."""
+                first_index: int = 0, precision=None, scratch: Optional[torch.Tensor] = None, fixup=None) -> None:
+    """``sample`` into caller-owned contiguous fp32 CUDA buffers ``out_dir`` [n,2|3] and ``out_pdf`` [n].
+    ``scratch``: caller-owned int32 CUDA buffer of ``sample_scratch_elems(n)`` elements; without it the call is the
+    single tensor-core launch (no fp32 fix-up)."""
     _require_cuda(wi, "sample_into")
     wi = _f32c(wi)
     n, cols = wi.shape[0], (2 if epilogue == EPI_RAW else 3)
+    _check_rows(wi, n, cols, "wi")
     for t, shape in ((out_dir, (n, cols)), (out_pdf, (n,))):
         if (not t.is_cuda) or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
             raise ValueError(f"bsdfdiff.sample_into: output must be a contiguous fp32 CUDA tensor of shape {shape}")
-    if T < 0 or (T == 0) != (flow.blob is None):
-        raise ValueError("T must be >= 1 (T == 0 only with NullFlow: base distribution alone)")
+    if scratch is not None and (scratch.dtype != torch.int32 or not scratch.is_cuda or not scratch.is_contiguous()
+                                or scratch.numel() < sample_scratch_elems(n)):
+        raise ValueError(f"bsdfdiff.sample_into: scratch must be a contiguous int32 CUDA tensor of >= "
+                         f"{sample_scratch_elems(n)} elements")
+    _check_flow(flow, T, "sample_into")
     if x0 is not None:
         x0 = _f32c(x0, wi.device)
+        _check_rows(x0, n, 2, "x0")
         seed, offset = 0, 0
     elif seed is None:
         seed, offset = next_philox(wi.device)
-    _sample_out_op(wi, flow.blob, base, x0, out_dir, out_pdf, _resolve_precision(precision), flow.domain, epilogue,
-                   int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index))
+    _sample_out_op(wi, flow.blob, base, x0, out_dir, out_pdf, scratch, _resolve_precision(precision), flow.domain,
+                   epilogue, int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index),
+                   _fix_thr(fixup))
 
 
 def pdf(wo: torch.Tensor, wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,
-        precision=None) -> torch.Tensor:
+        precision=None, fixup=None) -> torch.Tensor:
     _require_cuda(wi, "pdf")
     wi = _f32c(wi)
     wo = _f32c(wo, wi.device)
-    if T < 0 or (T == 0) != (flow.blob is None):
-        raise ValueError("T must be >= 1 (T == 0 only with NullFlow: base distribution alone)")
-    if wo.shape[0] != wi.shape[0]:
-        raise ValueError("wo and wi must have the same number of rows")
+    _check_flow(flow, T, "pdf")
+    cols = 2 if epilogue == EPI_RAW else 3
+    _check_rows(wi, wi.shape[0], cols, "wi")
+    _check_rows(wo, wi.shape[0], cols, "wo")
     return _pdf_op(wo, wi, flow.blob, base, _resolve_precision(precision), flow.domain, epilogue, int(T),
-                   flow.hidden, flow.n_hidden)
+                   flow.hidden, flow.n_hidden, _fix_thr(fixup))
+
+
+def base_log_prob(x: torch.Tensor, wi: torch.Tensor, base: torch.Tensor, domain: int) -> torch.Tensor:
+    """log p_base(x | wi) [n] for domain coordinates x, wi [n,2] (``D_base.log_prob``)."""
+    _require_cuda(wi, "base_log_prob")
+    wi = _f32c(wi)
+    x = _f32c(x, wi.device)
+    _check_rows(wi, wi.shape[0], 2, "wi")
+    _check_rows(x, wi.shape[0], 2, "x")
+    return _base_log_prob_op(x, wi, base, int(domain))
 
 
 def flow_forward(wi: torch.Tensor, flow, T: int, *, n: Optional[int] = None, wi_repeat: int = 1,
@@ -239,10 +348,16 @@ def flow_forward(wi: torch.Tensor, flow, T: int, *, n: Optional[int] = None, wi_
     """Forward-only T-step flow (dosampling).  -> (x_T [n,2], x0 [n,2])."""
     _require_cuda(wi, "flow_forward")
     wi = _f32c(wi)
+    _check_rows(wi, wi.shape[0], 2, "wi")
+    if flow.in_dim not in (25, 26):
+        raise ValueError(f"bsdfdiff.flow_forward: the flow nets take 25 or 26 inputs, got {flow.in_dim}")
     if n is None:
         n = wi.shape[0] * wi_repeat
+    if n > wi.shape[0] * wi_repeat:
+        raise ValueError(f"bsdfdiff.flow_forward: n = {n} exceeds rows * wi_repeat = {wi.shape[0] * wi_repeat}")
     if x0 is not None:
         x0 = _f32c(x0, wi.device)
+        _check_rows(x0, int(n), 2, "x0")
         seed, offset = 0, 0
     else:
         if base is None:

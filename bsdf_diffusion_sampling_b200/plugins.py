@@ -55,7 +55,7 @@ class NeuralBSDFSampler:
     """Fused sample / pdf for one material (one flow net + one base net)."""
 
     def __init__(self, kind: str, flow: weights.PackedFlow, base: torch.Tensor, T: Optional[int] = None,
-                 precision=None):
+                 precision=None, fixup=None):
         if kind not in _KINDS:
             raise ValueError(f"unknown plugin kind {kind!r}")
         self.kind = kind
@@ -66,6 +66,7 @@ class NeuralBSDFSampler:
         self.flow, self.base = flow, base
         self.T = int(T or t_default)
         self.precision = precision
+        self.fixup = fixup            # conditioning threshold of the tc16 fp32 fix-up (None: ops' default, 0: off)
 
     # -- construction -------------------------------------------------------------------------
     @classmethod
@@ -85,40 +86,51 @@ class NeuralBSDFSampler:
         """wi [N,3] local frame -> (wo [N,3], pdf_omega [N]) == (bs.wo, bs.pdf as first assigned)."""
         wo, pdf, _ = ops.sample(wi, self.flow, self.base, self.T, epilogue=self.epilogue, x0=x0, seed=seed,
                                 offset=offset, first_index=first_index, precision=self.precision,
-                                return_x0=False)
+                                return_x0=False, fixup=self.fixup)
         return wo, pdf
 
     def pdf(self, wi: torch.Tensor, wo: torch.Tensor) -> torch.Tensor:
         """(wi [N,3], wo [N,3]) -> pdf_omega [N] (MyBSDF.pdf incl. the cos/sin masks of the plugin kind)."""
-        return ops.pdf(wo, wi, self.flow, self.base, self.T, epilogue=self.epilogue, precision=self.precision)
+        return ops.pdf(wo, wi, self.flow, self.base, self.T, epilogue=self.epilogue, precision=self.precision,
+                       fixup=self.fixup)
 
     # -- host-buffer entry point (what a renderer that keeps its wavefront on the host calls) ---------
     def sample_host(self, wi_host: torch.Tensor, wo_host: torch.Tensor, pdf_host: torch.Tensor, *, seed: int,
-                    offset: int = 0, first_index: int = 0, chunk: int = 1 << 20, device=None) -> int:
+                    offset: int = 0, first_index: int = 0, chunk: int = 1 << 20, device=None,
+                    copy_only: bool = False) -> int:
         """Sample for ``wi_host`` [N,3] (pinned CPU memory), writing ``wo_host`` [N,3] / ``pdf_host`` [N]
         (pinned).  The batch is streamed in chunks over three CUDA streams so the H2D copy of chunk k+1,
-        the kernel of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full duplex).  All device
-        buffers (3 input + 3 output slots) are allocated once and reused -- nothing is allocated or freed
-        while the pipeline runs.  Philox counters are global row indices, so the result equals one
-        whole-batch launch.  Returns the number of kernel launches."""
+        the kernels of chunk k and the D2H copy of chunk k-1 overlap (PCIe is full duplex).  All device
+        buffers (3 input + 3 output slots + 3 fix-up scratch buffers) are allocated once and reused -- nothing is
+        allocated or freed while the pipeline runs -- and the slot-reuse events persist ACROSS calls, so the first
+        H2D copies of the next call run under the last D2H copies of this one (a renderer calling once per bounce
+        keeps the bus busy in both directions).  The caller's current stream waits for the results, the host does
+        not.  Philox counters are global row indices, so the result equals one whole-batch launch.
+        ``copy_only=True`` skips the kernels (same chunks, streams and copies): the PCIe ceiling of this pipeline.
+        Returns the number of kernel launches enqueued by this package (tensor-core + fix-up)."""
         device = torch.device(device or self.base.device)
         n = wi_host.shape[0]
         pipe = getattr(self, "_host_pipe", None)
-        if pipe is None or pipe[0] != chunk or pipe[1] != device:
-            bufs = [(torch.empty((chunk, 3), dtype=torch.float32, device=device),
-                     torch.empty((chunk, 3), dtype=torch.float32, device=device),
-                     torch.empty((chunk,), dtype=torch.float32, device=device)) for _ in range(3)]
-            pipe = self._host_pipe = (chunk, device, bufs, [torch.cuda.Stream(device) for _ in range(3)])
-        _, _, bufs, (s_in, s_k, s_out) = pipe
+        if pipe is None or pipe["chunk"] != chunk or pipe["device"] != device:
+            with torch.cuda.device(device):
+                bufs = [(torch.empty((chunk, 3), dtype=torch.float32, device=device),
+                         torch.empty((chunk, 3), dtype=torch.float32, device=device),
+                         torch.empty((chunk,), dtype=torch.float32, device=device),
+                         torch.empty((ops.sample_scratch_elems(chunk),), dtype=torch.int32, device=device))
+                        for _ in range(3)]
+                pipe = self._host_pipe = {"chunk": chunk, "device": device, "bufs": bufs,
+                                          "streams": [torch.cuda.Stream(device) for _ in range(3)],
+                                          "in_free": [None] * 3, "out_free": [None] * 3, "k": 0}
+        bufs, (s_in, s_k, s_out) = pipe["bufs"], pipe["streams"]
+        in_free, out_free = pipe["in_free"], pipe["out_free"]     # slot-reuse events, kept across calls
         cur = torch.cuda.current_stream(device)
-        for s in (s_in, s_k, s_out):
-            s.wait_stream(cur)
+        s_k.wait_stream(cur)                 # weights / anything the caller enqueued before this call
+        fix = ops.get_fixup_threshold() > 0 and ops._resolve_precision(self.precision) != ops.PREC_FP32
         launches = 0
-        in_free = [None, None, None]         # kernel that last read input slot j has finished
-        out_free = [None, None, None]        # D2H copies that last read output slot j have finished
-        for k, a in enumerate(range(0, n, chunk)):
-            b, j = min(n, a + chunk), k % 3
-            wi_dev, wo_dev, pdf_dev = bufs[j]
+        for a in range(0, n, chunk):
+            b, j = min(n, a + chunk), pipe["k"] % 3
+            pipe["k"] += 1
+            wi_dev, wo_dev, pdf_dev, scratch = bufs[j]
             with torch.cuda.stream(s_in):
                 if in_free[j] is not None:
                     s_in.wait_event(in_free[j])
@@ -129,10 +141,11 @@ class NeuralBSDFSampler:
                 s_k.wait_event(ev_in)
                 if out_free[j] is not None:
                     s_k.wait_event(out_free[j])
-                ops.sample_into(wi_dev[: b - a], self.flow, self.base, self.T, wo_dev[: b - a], pdf_dev[: b - a],
-                                epilogue=self.epilogue, seed=seed, offset=offset, first_index=first_index + a,
-                                precision=self.precision)
-                launches += 1
+                if not copy_only:
+                    ops.sample_into(wi_dev[: b - a], self.flow, self.base, self.T, wo_dev[: b - a], pdf_dev[: b - a],
+                                    epilogue=self.epilogue, seed=seed, offset=offset, first_index=first_index + a,
+                                    precision=self.precision, scratch=scratch)
+                    launches += 2 if fix else 1
                 ev_k = torch.cuda.Event()
                 ev_k.record(s_k)
                 in_free[j] = ev_k
@@ -144,7 +157,6 @@ class NeuralBSDFSampler:
                 ev_o.record(s_out)
                 out_free[j] = ev_o
         cur.wait_stream(s_out)
-        cur.wait_stream(s_k)
         return launches
 
     # -- small tensor helpers of the plugins ------------------------------------------------------

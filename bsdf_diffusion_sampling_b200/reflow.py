@@ -76,7 +76,11 @@ def load_pytorch_model_to_tinycuda(model: Network, state_dict, input_dims: int, 
     parts.append(nn.functional.pad(sd[-1], pad=(0, 0, 0, 16 - (output_dims % 16))).flatten())
     flat = torch.cat([p.detach().to("cpu", torch.float32) for p in parts]).half()
     with torch.no_grad():
-        model.params.data[...] = flat.to(model.params.device, model.params.dtype)
+        # copy_ on the Parameter itself bumps its version counter (a write through .data would not), and the packed
+        # blob is dropped explicitly: the next forward / dosampling call re-packs the new weights
+        model.params.copy_(flat.to(model.params.device, model.params.dtype))
+    model._packed = None
+    model._packed_sig = None
 
 
 def dosampling(batchsize: int, omega_i: torch.Tensor, T: int, pretrain_network, rectify_net, *,

@@ -29,7 +29,14 @@ class PackedFlow:
 
     @property
     def domain(self) -> int:
-        return _lib.DISK if self.in_dim == 25 else _lib.SPHERICAL
+        """Domain of the sampler nets; generic tcnn-style nets (any other in_dim) have none and only run through
+        ``ops.mlp_forward``."""
+        if self.in_dim == 25:
+            return _lib.DISK
+        if self.in_dim == 26:
+            return _lib.SPHERICAL
+        raise ValueError(f"flow net takes {self.in_dim} inputs: only the 25 (disk) or 26 (spherical) input sampler "
+                         "nets have a domain")
 
     def to(self, device) -> "PackedFlow":
         return PackedFlow(self.blob.to(device), self.in_dim, self.hidden, self.n_hidden)
@@ -98,6 +105,15 @@ def load_checkpoint(path: str) -> Dict[str, torch.Tensor]:
 
 # ---- per-module cache -----------------------------------------------------------------------
 _cache: "weakref.WeakKeyDictionary[torch.nn.Module, tuple]" = weakref.WeakKeyDictionary()
+
+
+def invalidate(module: torch.nn.Module) -> None:
+    """Drop the cached packing of ``module``.  Needed only after writing parameters through ``.data`` (which does not
+    bump the version counter the cache is keyed on); in-place ops, ``load_state_dict`` and optimiser steps do."""
+    _cache.pop(module, None)
+    if hasattr(module, "_packed"):
+        module._packed = None
+        module._packed_sig = None
 
 
 def _signature(module: torch.nn.Module, device) -> tuple:

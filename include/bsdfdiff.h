@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define BSDFDIFF_ABI_VERSION 1
+#define BSDFDIFF_ABI_VERSION 2
 
 /* domains (state parameterisation of the flow) */
 #define BSDFDIFF_DISK       0   /* state = projected (x,y) on the unit disk; net input 25 = [x,y,alpha,PE5(wi)] */
@@ -56,8 +56,10 @@ extern "C" {
 #define BSDFDIFF_PREC_TC16  1   /* tcgen05: fp16 operands, fp32 TMEM accumulators (throughput path)             */
 #define BSDFDIFF_PREC_TC16_EXP 2 /* as TC16 but SiLU via fp32 exp instead of tanh.approx (accuracy cross-check)  */
 
-/* error codes */
+/* return codes: 0 ok, > 0 ok with a note, < 0 error */
 #define BSDFDIFF_OK            0
+#define BSDFDIFF_OK_FP32_REROUTE 1 /* a PREC_TC16* call whose net shape the tensor-core kernel does not cover (more than 6
+                                      hidden layers, sample/pdf with a 64-wide net) ran on the PREC_FP32 CUDA-core kernel  */
 #define BSDFDIFF_EINVAL       -1   /* bad argument (null pointer, unsupported shape, T < 1, ...) */
 #define BSDFDIFF_EUNSUPPORTED -2   /* shape not supported by the requested precision path        */
 #define BSDFDIFF_ECUDA        -3   /* a CUDA runtime call failed (see bsdfdiff_last_cuda_error)   */
@@ -95,12 +97,31 @@ int    bsdfdiff_pack_flow_tcnn(const float* tcnn_params /*host, fp32 copy of .pa
 int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
                     const float* wi, const void* flow_packed, int hidden, int n_hidden,
                     const float* base_params, const float* x0_replay, uint64_t seed, uint64_t offset, int64_t first_index,
-                    float* out_dir, float* out_pdf, float* out_x0, void* cuda_stream);
+                    float* out_dir, float* out_pdf, float* out_x0, float fix_threshold, void* fix_scratch,
+                    void* cuda_stream);
+
+/* ---- conditioning-triggered fp32 fix-up of the PREC_TC16 path (fix_threshold, fix_scratch above and below) ----
+ * pdf = p_base / prod_t det J_t: where a step determinant is close to zero (or the later steps amplify an early
+ * state error, or pdf()'s base density is steep at the flow's end point) fp16-operand arithmetic cannot meet the
+ * stated pdf tolerance -- an ideal fp16-operand / fp32-accumulate evaluation misses it too (profiles/r2_emulate_tc16.txt).
+ * With fix_threshold > 0 the tensor-core kernel computes, per query, the conditioning weight
+ *     w = min(1, min_t|det_t| / 0.2) * min(1, 16 / prod_t max(1, sigma_max(J_t))) [* min(1, 25 / |grad log p_base|), pdf()]
+ * and appends every row with w < fix_threshold to a device list; a second launch on the same stream recomputes
+ * exactly those rows with the PREC_FP32 kernel (same base sample: x0_replay, or out_x0, one of which is then
+ * REQUIRED for bsdfdiff_sample).  No host synchronisation; CUDA-graph capturable (memset + 2 kernels).
+ * fix_scratch: device buffer of bsdfdiff_fixup_scratch_bytes(n) bytes; after the call its first uint32 holds the
+ * number of recomputed rows.  fix_threshold = 0 (or PREC_FP32): single launch, scratch may be NULL. */
+size_t bsdfdiff_fixup_scratch_bytes(int64_t n);
 
 /* ---- pdf: reverse flow from wo; pdf = p_base(x_T | wi) * prod det(I - dD/dx / T) ---------------------------- */
 int bsdfdiff_pdf(int precision, int domain, int epilogue, int T, int64_t n,
                  const float* wo, const float* wi, const void* flow_packed, int hidden, int n_hidden,
-                 const float* base_params, float* out_pdf, void* cuda_stream);
+                 const float* base_params, float* out_pdf, float fix_threshold, void* fix_scratch, void* cuda_stream);
+
+/* ---- log p_base(x | wi): D_base.log_prob (rendering/utils/model.py:393-398 disk, :308-317 spherical) ---------
+ * x, wi: [n,2] domain coordinates.  Returned as a LOG density (no exp/log round trip: finite where p underflows). */
+int bsdfdiff_base_log_prob(int domain, int64_t n, const float* x, const float* wi, const float* base_params,
+                           float* out_logp, void* cuda_stream);
 
 /* ---- forward-only flow (reflow "dosampling"): x_T = x0 + sum_t D(x_t, t/T | wi)/T, no pdf -------------------
  * wi: [n_wi,2] domain coords; query i uses wi[i / wi_repeat] (repeat_interleave without materialising it).

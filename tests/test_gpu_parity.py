@@ -5,8 +5,16 @@ Tolerances (stated up front):
   fp32 CUDA-core path vs reference/oracle:  |d x| <= 2e-5 * max(1,|x|),  pdf rel err p99 <= 1e-4 (goldens: 2e-4,
       the golden itself carries the reference's own fp32 rounding)
   tc16 tensor-core path vs reference/oracle: |d x| median <= 5e-4, p99 <= 1e-2; pdf rel err median <= 5e-3,
-      p99 <= 5e-2; <= 0.1 % of queries may exceed 50 % rel err (near-singular step determinant) but must stay finite
+      p99 <= 5e-2; <= 0.1 % of queries may exceed 50 % rel err (near-singular step determinant) but must stay finite.
+      The bar is applied to the RAW relative error of every query.  "tc16" below is the shipped product path: the
+      tensor-core kernel plus its conditioning-triggered fp32 fix-up pass (include/bsdfdiff.h; default threshold
+      0.25) -- fp16-operand arithmetic alone cannot meet the bar on ill-conditioned materials, not even with ideal
+      fp32 accumulation (profiles/r2_emulate_tc16.txt: spherical_ilm_solo_m_68_rgb p99 1.5e-1).  The oracle's
+      conditioning weight is printed as a diagnostic only; no assertion is scaled by it.
 """
+import os
+import subprocess
+
 import numpy as np
 import pytest
 import torch
@@ -39,14 +47,9 @@ def check_x(x, ref, prec):
         assert np.quantile(err, 0.99) <= 1e-2, f"p99 |dx| = {np.quantile(err, 0.99)}"
 
 
-def check_pdf(p, ref, prec, golden=False, mindet=None):
-    """``mindet`` = the oracle's per-query conditioning weight in (0,1] (oracle/bsdf_oracle.c, euler()):
-    pdf = p0 / prod_t det_t, so a rounding error eps in a step determinant is a RELATIVE pdf error
-    eps/|det_t| (factor min(1, min|det|/0.2)); a state error made in an early step is amplified by the later
-    steps' Jacobians (factor min(1, 16/prod sigma_max(J_t)) -- reverse flows of strongly contracting nets
-    reach 100x+); pdf() also evaluates the base density at the flow's end point (factor
-    min(1, 25/|grad log p_base|)).  The reduced-precision bar is stated per unit of condition number: it
-    applies as written to well-conditioned queries (weight 1) and to weight * error otherwise."""
+def check_pdf(p, ref, prec, golden=False, mindet=None, what=""):
+    """RAW relative error against the stated bar.  ``mindet`` (the oracle's conditioning weight in (0,1]) only feeds a
+    printed diagnostic: the weighted p99 next to the raw one."""
     ok = np.isfinite(ref)
     assert np.isfinite(p[ok]).mean() > 0.999
     r = rel(p[ok], ref[ok])
@@ -55,9 +58,11 @@ def check_pdf(p, ref, prec, golden=False, mindet=None):
         assert np.quantile(r, 0.99) <= (2e-4 if golden else 1e-4), f"p99 rel = {np.quantile(r, 0.99)}"
         assert np.median(r) <= 2e-5
     else:
+        fin = np.isfinite(r)
         if mindet is not None:
-            r = r * mindet[ok]
-        r = r[np.isfinite(r)]
+            print(f"[tc16 {what}] raw pdf rel p99 {np.quantile(r[fin], 0.99):.2e}, "
+                  f"conditioning-weighted p99 {np.quantile((r * mindet[ok])[fin], 0.99):.2e}")
+        r = r[fin]
         assert np.median(r) <= 5e-3, f"median rel = {np.median(r)}"
         assert np.quantile(r, 0.99) <= 5e-2, f"p99 rel = {np.quantile(r, 0.99)}"
         assert (r > 0.5).mean() <= 1e-3
@@ -91,7 +96,7 @@ def test_sample_golden(pkg, path, prec):
     assert torch.equal(x0.cpu(), torch.from_numpy(z["x0"]))
     check_x(x.cpu().numpy(), z["x"], prec)
     _, _, mindet = C.sample(flow, base, z["wi"], int(z["T"]), z["x0"], with_mindet=True)
-    check_pdf(pdf.cpu().numpy(), z["pdf_sample"], prec, golden=True, mindet=mindet)
+    check_pdf(pdf.cpu().numpy(), z["pdf_sample"], prec, golden=True, mindet=mindet, what="sample " + os.path.basename(path)[:-4])
     if prec == "fp32":
         assert np.array_equal(np.sign(pdf.cpu().numpy()), np.sign(z["pdf_sample"]))
 
@@ -102,7 +107,39 @@ def test_pdf_golden(pkg, path, prec):
     flow, base, z, pf, pb = load(pkg, path)
     p = pkg.ops.pdf(cu(z["wo_eval"]), cu(z["wi_eval"]), pf, pb, int(z["T"]), precision=prec)
     _, mindet = C.pdf(flow, base, z["wo_eval"], z["wi_eval"], int(z["T"]), with_mindet=True)
-    check_pdf(p.cpu().numpy(), z["pdf_eval"], prec, golden=True, mindet=mindet)
+    check_pdf(p.cpu().numpy(), z["pdf_eval"], prec, golden=True, mindet=mindet, what="pdf() " + os.path.basename(path)[:-4])
+
+
+@pytest.mark.parametrize("path", GOLDEN_FILES, ids=golden_ids())
+def test_fixup_pass_recomputes_exactly_the_flagged_rows(pkg, path):
+    """The tc16 product path = tensor-core kernel + fp32 fix-up of the ill-conditioned rows.  Rows the kernel did NOT
+    flag are bit-identical to the single-launch result (fixup=0); flagged rows are bit-identical to the fp32 kernel on
+    the same base sample; a lower threshold flags a subset."""
+    flow, base, z, pf, pb = load(pkg, path)
+    T, wi, x0 = int(z["T"]), cu(z["wi"]), cu(z["x0"])
+    plain = pkg.ops.sample(wi, pf, pb, T, x0=x0, precision="tc16", fixup=0.0)
+    fixed = pkg.ops.sample(wi, pf, pb, T, x0=x0, precision="tc16", fixup=0.25)
+    n_fix = pkg.ops.last_fixup_count()
+    f32 = pkg.ops.sample(wi, pf, pb, T, x0=x0, precision="fp32")
+    same = (fixed[1] == plain[1]) & (fixed[0] == plain[0]).all(1)
+    as32 = (fixed[1] == f32[1]) & (fixed[0] == f32[0]).all(1)
+    assert bool((same | as32).all())
+    assert int((~same).sum()) <= n_fix <= int(as32.sum())
+    assert n_fix <= 0.12 * wi.shape[0], "the fix-up is for the ill-conditioned tail, not the bulk"
+    pkg.ops.sample(wi, pf, pb, T, x0=x0, precision="tc16", fixup=0.1)
+    assert pkg.ops.last_fixup_count() <= n_fix
+    # Philox path (no replayed x0): the fix-up pass replays the base sample the tensor-core kernel drew
+    a = pkg.ops.sample(wi, pf, pb, T, seed=9, offset=4, precision="tc16", fixup=0.25)
+    b = pkg.ops.sample(wi, pf, pb, T, x0=a[2], precision="tc16", fixup=0.25)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # pdf(): same contract
+    wo, wie = cu(z["wo_eval"]), cu(z["wi_eval"])
+    p0 = pkg.ops.pdf(wo, wie, pf, pb, T, precision="tc16", fixup=0.0)
+    p1 = pkg.ops.pdf(wo, wie, pf, pb, T, precision="tc16", fixup=0.25)
+    n_fix = pkg.ops.last_fixup_count()
+    p32 = pkg.ops.pdf(wo, wie, pf, pb, T, precision="fp32")
+    assert bool(((p1 == p0) | (p1 == p32)).all()) and int((p1 != p0).sum()) <= n_fix
+    print(f"[fixup {os.path.basename(path)[:-4]}] pdf() rows recomputed: {n_fix} of {wo.shape[0]}")
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
@@ -148,10 +185,16 @@ def test_reference_named_entry_points(pkg):
         c, _ = fs(B, D, wi, precision="fp32")
         assert torch.equal(a, b) and not torch.equal(a, c)
         # base net alone through the library (T = 0)
-        lp = B.log_prob(cu(z["x0"]), wi).cpu().numpy()
-        want = (O.base_logprob_disk if T == 4 else O.base_logprob_spherical)(base, z["x0"], z["wi"])
-        assert np.quantile(np.abs(lp - want), 0.99) <= 1e-4 * (1 + np.abs(want).max())
-        assert B.sample(wi).shape == (wi.shape[0], 2)
+        with torch.no_grad():
+            lp = B.log_prob(cu(z["x0"]), wi).cpu().numpy()
+            want = (O.base_logprob_disk if T == 4 else O.base_logprob_spherical)(base, z["x0"], z["wi"])
+            assert np.quantile(np.abs(lp - want), 0.99) <= 1e-4 * (1 + np.abs(want).max())
+            assert B.sample(wi).shape == (wi.shape[0], 2)
+            # the kernel returns the LOG density: finite where exp() underflows (model.py:393-398 returns logs too)
+            far = B.log_prob(cu(z["x0"]) + 400.0, wi)
+            assert torch.isfinite(far).all() and (far < -1000).all()
+        with pytest.raises(RuntimeError, match="inference-only"):
+            B.log_prob(cu(z["x0"]), wi)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -326,8 +369,14 @@ def test_edge_sizes_and_layouts(pkg, prec):
         x, pdf, _ = pkg.ops.sample(cu(wi_all[:n]), pf, pb, 4, x0=cu(x0_all[:n]), precision=prec)
         assert x.shape == (n, 2) and pdf.shape == (n,)
         if n:
-            check_x(x.cpu().numpy(), ref_x[:n], prec) if n > 100 else None
-            assert np.isfinite(x.cpu().numpy()).all()
+            xn, pn = x.cpu().numpy(), pdf.cpu().numpy()
+            assert np.isfinite(xn).all()
+            if prec == "fp32":
+                check_x(xn, ref_x[:n], prec)
+                assert np.abs(pn - ref_pdf[:n]).max() <= 2e-4 * np.abs(ref_pdf[:n]).max()
+            else:       # quantile bars need a population: small n is checked row by row against the p99 bars
+                assert np.abs(xn - ref_x[:n]).max() <= 1e-2
+                assert (rel(pn, ref_pdf[:n]) <= 5e-2).mean() >= (0.98 if n > 100 else 1.0)
     # non-contiguous / float64 inputs are accepted (converted), like tensors arriving from Dr.Jit
     wi_nc = cu(np.concatenate([wi_all, wi_all], 1))[:, :2].double()
     x, pdf, _ = pkg.ops.sample(wi_nc, pf, pb, 4, x0=cu(x0_all), precision=prec)
@@ -350,6 +399,10 @@ def test_edge_sizes_and_layouts(pkg, prec):
     with pytest.raises(ValueError):
         pkg.ops.pdf(cu(wi_all[:5]), cu(wi_all), pf, pb, 4, precision=prec)
     with pytest.raises(ValueError):
+        pkg.ops.sample(cu(wi_all), pf, pb, 4, x0=cu(x0_all[:-1]), precision=prec)     # x0 row count
+    with pytest.raises(ValueError):
+        pkg.ops.sample(cu(np.concatenate([wi_all, wi_all[:, :1]], 1)), pf, pb, 4, precision=prec)   # [n,3] into EPI_RAW
+    with pytest.raises(ValueError):
         pkg.plugins.NeuralBSDFSampler("spherical", pf, pb)           # disk net in a spherical plugin
 
 
@@ -366,6 +419,21 @@ def test_cuda_graph_capture(pkg, prec):
     g.replay()
     torch.cuda.synchronize()
     check_x(out[0].cpu().numpy(), z["x"], prec)
+    # Philox path: (seed, offset) are host values -> explicit ones capture (memset + kernel + fix-up kernel replay
+    # bit-identically); drawing them from torch's generator inside a capture would bake them in, so it raises
+    eager = pkg.ops.sample(wi, pf, pb, 8, seed=5, offset=12, precision=prec)
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        cap = pkg.ops.sample(wi, pf, pb, 8, seed=5, offset=12, precision=prec)
+    g2.replay()
+    g2.replay()
+    torch.cuda.synchronize()
+    for u, v in zip(eager, cap):
+        assert torch.equal(u, v)
+    with pytest.raises(RuntimeError, match="not CUDA-graph capturable"):
+        with torch.cuda.graph(torch.cuda.CUDAGraph()):
+            pkg.ops.sample(wi, pf, pb, 8, precision=prec)
+    torch.cuda.synchronize()
 
 
 def test_multi_material_wavefront(pkg):
@@ -399,6 +467,163 @@ def test_multi_material_wavefront(pkg):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     with pytest.raises(IndexError):
         mm.sample(wi, mid + 1, seed=3)
+
+
+def test_checkpoint_loading_and_plugin_helpers(pkg, tmp_path):
+    """from_checkpoints / checkpoint_paths on .pth files laid out like rendering/checkpoints_new (incl. the quirk that
+    the measured-spherical plugin loads the *_disk* pretrain checkpoint), firefly_clamp and eta_and_type."""
+    P = pkg.plugins
+    for kind, path, mat in (("disk", DISK_FILE, "matA"), ("spherical", SPH_FILE, "matA"), ("bsdf", BSDF_FILE, 7)):
+        flow, base, z, pf, pb = load(pkg, path)
+        fp, bp = P.checkpoint_paths(kind, mat, str(tmp_path))
+        for f in (fp, bp):
+            os.makedirs(os.path.dirname(f), exist_ok=True)
+        names = [f"linear{i + 1}.weight" for i in range(len(flow.layers) - 1)] + ["output.weight"]
+        torch.save({k: torch.from_numpy(w) for k, w in zip(names, flow.layers)}, fp)
+        torch.save({"linear1.weight": torch.from_numpy(base.w1), "linear1.bias": torch.from_numpy(base.b1),
+                    "output.weight": torch.from_numpy(base.wo), "output.bias": torch.from_numpy(base.bo)}, bp)
+        s = P.NeuralBSDFSampler.from_checkpoints(kind, mat, str(tmp_path))
+        assert torch.equal(s.flow.blob, pf.blob) and torch.equal(s.base, pb) and s.T == (4 if kind == "disk" else 8)
+        wi3 = cu(random_dirs(1000, np.random.default_rng(1), full_sphere=(kind == "bsdf")))
+        wo, pdf = s.sample(wi3, seed=3)
+        ref = P.NeuralBSDFSampler(kind, pf, pb).sample(wi3, seed=3)
+        assert torch.equal(wo, ref[0]) and torch.equal(pdf, ref[1])
+        # firefly clamp: luminance(value) >= 30 (measured) / red >= 3.5 (bsdf) zeroes the pdf
+        value = torch.rand(1000, 3, device="cuda") * (60.0 if kind != "bsdf" else 7.0)
+        clamped = s.firefly_clamp(pdf, value)
+        key = value[:, 0] if kind == "bsdf" else (0.2126 * value[:, 0] + 0.7152 * value[:, 1] + 0.0722 * value[:, 2])
+        thr = 3.5 if kind == "bsdf" else 30.0
+        assert torch.equal(clamped, torch.where(key < thr, pdf, torch.zeros_like(pdf)))
+        assert 0 < int((clamped == 0).sum()) < 1000
+    eta, typ = P.NeuralBSDFSampler.eta_and_type(wo)
+    up = wo[:, 2] > 0
+    assert torch.equal(eta, torch.where(up, 1.0, 1.788)) and torch.equal(typ, torch.where(up, 8, 16))
+    assert bool(up.any()) and bool((~up).any())                     # the bsdf kind samples both hemispheres
+
+
+def test_sharded_sampler_on_gpu(pkg):
+    """ShardedSampler.sample_local / sample with explicit (rank, world): the shards of a 2- and 3-way split
+    concatenate to the single-launch result bit for bit (Philox counter = global row index)."""
+    flow, base, z, pf, pb = load(pkg, SPH_FILE)
+    s = pkg.plugins.NeuralBSDFSampler("spherical", pf, pb)
+    n = 70_001
+    wi3 = cu(random_dirs(n, np.random.default_rng(4)))
+    whole = s.sample(wi3, seed=77, offset=8)
+    for world in (2, 3):
+        parts = []
+        for r in range(world):
+            ss = pkg.sharding.ShardedSampler(s, rank=r, world=world)
+            a, b = ss.local_range(n)
+            parts.append(ss.sample_local(wi3[a:b], n, seed=77, offset=8))
+            with pytest.raises(ValueError):
+                ss.sample_local(wi3[a:b + 1], n, seed=77)
+        assert torch.equal(torch.cat([p[0] for p in parts]), whole[0])
+        assert torch.equal(torch.cat([p[1] for p in parts]), whole[1])
+    ss = pkg.sharding.ShardedSampler(s, rank=1, world=2)
+    a, b = ss.local_range(n)
+    wo, pdf = ss.sample(wi3, seed=77, offset=8, gather=False)
+    assert torch.equal(wo, whole[0][a:b]) and torch.equal(pdf, whole[1][a:b])
+    assert torch.equal(ss.pdf_local(wi3[a:b], wo), s.pdf(wi3[a:b], wo))
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import bsdf_diffusion_sampling_b200 as pkg2
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    flow, base, z = O.load_material_npz(DISK_FILE)
+    dev = torch.device("cuda", rank)
+    pf = pkg2.weights.pack_flow_layers(flow.layers, dev)
+    pb = pkg2.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, dev)
+    s = pkg2.plugins.NeuralBSDFSampler("disk", pf, pb)
+    n = 40_001
+    wi3 = torch.from_numpy(random_dirs(n, np.random.default_rng(8))).to(dev)
+    ss = pkg2.sharding.ShardedSampler(s)
+    wo, pdf = ss.sample(wi3, seed=5, gather=True)                      # all_gather_into_tensor over NCCL
+    ref = s.sample(wi3, seed=5)
+    q.put((rank, ss.world, bool(torch.equal(wo, ref[0]) and torch.equal(pdf, ref[1]))))
+    dist.destroy_process_group()
+
+
+def test_sharded_gather_over_nccl_world2(pkg):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, 2, True), (1, 2, True)]
+
+
+def test_tmem_aliasing_build_is_bit_identical(pkg):
+    """The shipped TMEM map lets the u-tangent operand alias the v-tangent accumulator (four tiles in flight instead of
+    three).  BSDFDIFF_TC_NOALIAS builds the non-overlapping 144-column map; both libraries must agree bit for bit."""
+    import ctypes
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_path = os.path.join(root, "variants", "lib_noalias.so")
+    srcs = [os.path.join(root, "bsdf_diffusion_sampling_b200", "csrc", f) for f in os.listdir(
+        os.path.join(root, "bsdf_diffusion_sampling_b200", "csrc")) if f.endswith((".cu", ".cuh"))]
+    if not os.path.exists(lib_path) or os.path.getmtime(lib_path) < max(os.path.getmtime(f) for f in srcs):
+        subprocess.check_call(["bash", os.path.join(root, "profiles", "build_variant.sh"), "noalias",
+                               "-DBSDFDIFF_TC_NOALIAS"],
+                              stdout=subprocess.DEVNULL)
+    alt = ctypes.CDLL(lib_path)
+    L = pkg._lib
+    alt.bsdfdiff_sample.argtypes = L.lib.bsdfdiff_sample.argtypes
+    alt.bsdfdiff_pdf.argtypes = L.lib.bsdfdiff_pdf.argtypes
+    for path in (DISK_FILE, BSDF_FILE):
+        flow, base, z, pf, pb = load(pkg, path)
+        T, n = int(z["T"]), z["wi"].shape[0]
+        wi, x0 = cu(z["wi"]), cu(z["x0"])
+        ref = pkg.ops.sample(wi, pf, pb, T, x0=x0, precision="tc16", fixup=0.0)
+        out_x = torch.empty(n, 2, device="cuda")
+        out_p = torch.empty(n, device="cuda")
+        rc = alt.bsdfdiff_sample(L.PREC_TC16, pf.domain, 0, T, n, wi.data_ptr(), pf.blob.data_ptr(), pf.hidden,
+                                 pf.n_hidden, pb.data_ptr(), x0.data_ptr(), 0, 0, 0, out_x.data_ptr(), out_p.data_ptr(),
+                                 None, 0.0, None, torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(out_x, ref[0]) and torch.equal(out_p, ref[1])
+        wo, wie = cu(z["wo_eval"]), cu(z["wi_eval"])
+        refp = pkg.ops.pdf(wo, wie, pf, pb, T, precision="tc16", fixup=0.0)
+        rc = alt.bsdfdiff_pdf(L.PREC_TC16, pf.domain, 0, T, n, wo.data_ptr(), wie.data_ptr(), pf.blob.data_ptr(),
+                              pf.hidden, pf.n_hidden, pb.data_ptr(), out_p.data_ptr(), 0.0, None,
+                              torch.cuda.current_stream().cuda_stream)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(out_p, refp)
+
+
+def test_unsupported_tensor_core_shape_reports_its_reroute(pkg):
+    """sample() with a 64-wide net is not covered by the tcgen05 kernel: the library runs its fp32 CUDA-core kernel
+    and SAYS so (BSDFDIFF_OK_FP32_REROUTE -> _lib.fp32_reroutes); BSDFDIFF_STRICT_TC=1 makes it an error."""
+    rng = np.random.default_rng(3)
+    layers = [rng.normal(0, 0.2, (64, 25)).astype(np.float32), rng.normal(0, 0.15, (64, 64)).astype(np.float32),
+              rng.normal(0, 0.1, (2, 64)).astype(np.float32)]
+    pf = pkg.weights.pack_flow_layers(layers, "cuda")
+    flow, base, z, _, pb = load(pkg, DISK_FILE)
+    wi, x0 = cu(z["wi"][:512]), cu(z["x0"][:512])
+    before = pkg._lib.fp32_reroutes
+    a = pkg.ops.sample(wi, pf, pb, 4, x0=x0, precision="tc16")
+    assert pkg._lib.fp32_reroutes == before + 1
+    b = pkg.ops.sample(wi, pf, pb, 4, x0=x0, precision="fp32")
+    assert pkg._lib.fp32_reroutes == before + 1 and torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    os.environ["BSDFDIFF_STRICT_TC"] = "1"
+    try:
+        with pytest.raises(pkg._lib.BsdfDiffError, match="STRICT_TC"):
+            pkg.ops.sample(wi, pf, pb, 4, x0=x0, precision="tc16")
+    finally:
+        del os.environ["BSDFDIFF_STRICT_TC"]
 
 
 # ------------------------------------------------------------------------------------------------

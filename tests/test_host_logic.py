@@ -22,15 +22,16 @@ def test_every_declared_symbol_is_exported(built_lib):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/bsdfdiff.h but not exported"
     assert set(built_lib._lib.EXPORTS) == declared
-    assert built_lib._lib.lib.bsdfdiff_abi_version() == 1
+    assert built_lib._lib.lib.bsdfdiff_abi_version() == 2
     assert built_lib._lib.lib.bsdfdiff_error_string(-2).decode().startswith("shape not supported")
 
 
 def _unpack_header(blob):
     import struct
-    magic, in_dim, H, nh, dom, off32, n32, off16, n16, total, off_aux, n_aux = struct.unpack("<I4i7I", blob[:48])
+    magic, in_dim, H, nh, dom, off32, n32, off16, n16, total = struct.unpack("<I4i5I", blob[:40])
+    assert blob[40:64] == bytes(24)                                  # reserved words stay zero
     return dict(magic=magic, in_dim=in_dim, H=H, nh=nh, dom=dom, off32=off32, n32=n32, off16=off16, n16=n16,
-                total=total, off_aux=off_aux, n_aux=n_aux)
+                total=total)
 
 
 @pytest.mark.parametrize("path", [DISK_FILE, BSDF_FILE])
@@ -73,8 +74,7 @@ def test_pack_flow_layout(built_lib, path):
     out = f16[2 * H * 32 + 2 * (nh - 1) * H * H:]
     assert (at(out[: 16 * H], 1, 17, 16), at(out[16 * H:], 1, 17, 16)) == hi_lo(flow.layers[-1][1, 17])
     assert at(out, 2, 3, 16) == 0 and out.size == 2 * 16 * H
-    aux = np.frombuffer(blob, np.float32, h["n_aux"] // 4, h["off_aux"])
-    assert np.array_equal(aux[:H], (0.5 * w1[:, 0]).astype(np.float16).astype(np.float32))
+    assert h["off16"] + -(-h["n16"] // 128) * 128 == h["total"]       # nothing follows the fp16 image
 
 
 def test_pack_flow_tcnn_equals_pack_from_layers(built_lib):
@@ -95,14 +95,33 @@ def test_argument_validation_without_gpu(built_lib):
     with pytest.raises(L.BsdfDiffError):
         built_lib.weights.pack_base_arrays(np.zeros((16, 14)), np.zeros(16), np.zeros((4, 16)), np.zeros(3), "cpu")
     # invalid arguments are rejected before any CUDA call
-    assert L.lib.bsdfdiff_sample(0, 0, 0, 4, 16, None, None, 32, 3, None, None, 0, 0, 0, None, None, None, None) == -1
-    assert L.lib.bsdfdiff_sample(0, 0, 2, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, None, None) == -1  # sph epilogue on disk
-    assert L.lib.bsdfdiff_pdf(0, 1, 0, -1, 16, 1, 1, 1, 32, 4, 1, 1, None) == -1
+    assert L.lib.bsdfdiff_sample(0, 0, 0, 4, 16, None, None, 32, 3, None, None, 0, 0, 0, None, None, None, 0.0, None,
+                                 None) == -1
+    assert L.lib.bsdfdiff_sample(0, 0, 2, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, None, 0.0, None,
+                                 None) == -1                          # spherical epilogue on a disk net
+    assert L.lib.bsdfdiff_pdf(0, 1, 0, -1, 16, 1, 1, 1, 32, 4, 1, 1, 0.0, None, None) == -1
+    # the fix-up needs its scratch buffer, and (sample) a base sample to replay
+    assert L.lib.bsdfdiff_sample(1, 0, 0, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, 1, 0.25, None, None) == -1
+    assert L.lib.bsdfdiff_sample(1, 0, 0, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, None, 0.25, 1, None) == -1
+    assert L.lib.bsdfdiff_base_log_prob(2, 16, 1, 1, 1, 1, None) == -1
+    assert L.lib.bsdfdiff_fixup_scratch_bytes(1000) == 16 + 4000
+    assert L.lib.bsdfdiff_error_string(1).decode().startswith("ok (")
     # CPU tensors raise: there is no CPU path
     flow, base, z = O.load_material_npz(DISK_FILE)
     pf = built_lib.weights.pack_flow_layers(flow.layers, "cpu")
     with pytest.raises(RuntimeError, match="no CPU path"):
         built_lib.ops.sample(torch.zeros(4, 2), pf, torch.zeros(308), 4, x0=torch.zeros(4, 2))
+    # generic tcnn-style nets (in_dim not 25 / 26) are mlp_forward-only: PackedFlow.domain refuses to guess
+    odd = built_lib.weights.pack_flow_layers([np.zeros((32, 24), np.float32), np.zeros((2, 32), np.float32)], "cpu")
+    with pytest.raises(ValueError, match="25 .disk. or 26"):
+        odd.domain
+    # checkpoint_paths: the measured-spherical plugin loads the *_disk* pretrain checkpoint (brdf_measured_spherical.py:59)
+    cp = built_lib.plugins.checkpoint_paths
+    assert cp("disk", "m", "r") == ("r/m_disk/brdf_rectify_networkm.pth", "r/m_disk/brdf_pretrain_networkm.pth")
+    assert cp("spherical", "m", "r") == ("r/m_spherical/brdf_rectify_networkm.pth", "r/m_disk/brdf_pretrain_networkm.pth")
+    assert cp("bsdf", 3, "r") == ("r/bsdf_3_spherical/brdf_rectify_network3.pth", "r/bsdf_3_spherical/brdf_pretrain_network3.pth")
+    with pytest.raises(ValueError):
+        cp("nope", "m")
 
 
 def test_multi_material_bucketing_without_gpu(built_lib):
@@ -161,9 +180,61 @@ def test_tcnn_network_shim_layout(built_lib):
     r.load_pytorch_model_to_tinycuda(net, sd, 25, 2)
     want = O.pack_tcnn_params(flow.layers, 25, 2).astype(np.float32)
     assert np.array_equal(net.params.detach().numpy(), want)
+    # loading a second material into the same Network must not serve the stale packed blob
+    first = net.packed("cpu")
+    assert net.packed("cpu") is first
+    sd2 = {k: 2.0 * v for k, v in sd.items()}
+    r.load_pytorch_model_to_tinycuda(net, sd2, 25, 2)
+    second = net.packed("cpu")
+    assert second is not first and not torch.equal(second.blob, first.blob)
+    net.params.data[0] = 123.0                                      # a raw .data write does not bump the version ...
+    built_lib.weights.invalidate(net)                               # ... so the explicit helper drops the cache
+    assert net.packed("cpu") is not second
     with pytest.raises(RuntimeError):
         r.Network(25, 2, {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
                           "n_neurons": 32, "n_hidden_layers": 3})
+
+
+def test_model_modules_are_inference_only(built_lib):
+    """forward / sample / log_prob are detached library calls: with autograd on and trainable parameters they raise
+    instead of returning values a training loop could not backpropagate through."""
+    m = built_lib.model
+    net = m.NN_cond_pos_simpler(input_dim=5, output_dim=2, N_NEURONS=32, POSITIONAL_ENCODING_BASIS_NUM=5)
+    b = m.NN_cond_pretrain_disk_one(input_dim=2, N_NEURONS=16, POSITIONAL_ENCODING_BASIS_NUM=3)
+    x = torch.zeros(4, 2)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        net(x, torch.zeros(4, 1), x)
+    with pytest.raises(RuntimeError, match="inference-only"):
+        b.log_prob(x, x)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="no CPU path"):     # past the guard: CPU tensors still raise
+        b.log_prob(x, x)
+
+
+def test_ops_shape_validation_without_gpu(built_lib):
+    """Shape mismatches are rejected on the host before any pointer reaches the library (they would be silent
+    out-of-bounds device reads otherwise)."""
+    ops = built_lib.ops
+    flow, base, _ = O.load_material_npz(DISK_FILE)
+    pf = built_lib.weights.pack_flow_layers(flow.layers, "cpu")
+
+    class FakeCuda(torch.Tensor):
+        is_cuda = True
+
+    def fake(*shape):
+        return torch.zeros(*shape).as_subclass(FakeCuda)
+
+    with pytest.raises(ValueError, match="wi must have shape"):
+        ops.sample(fake(8, 3), pf, torch.zeros(308), 4, x0=fake(8, 2))               # raw epilogue wants [n,2]
+    with pytest.raises(ValueError, match="wi must have shape"):
+        ops.sample(fake(8, 2), pf, torch.zeros(308), 4, epilogue=ops.EPI_DISK, x0=fake(8, 2))
+    with pytest.raises(ValueError, match="x0 must have shape"):
+        ops.sample(fake(8, 2), pf, torch.zeros(308), 4, x0=fake(7, 2))
+    with pytest.raises(ValueError, match="wo must have shape"):
+        ops.pdf(fake(7, 2), fake(8, 2), pf, torch.zeros(308), 4)
+    with pytest.raises(ValueError, match="exceeds rows"):
+        ops.flow_forward(fake(8, 2), pf, 4, n=100, wi_repeat=2, x0=fake(100, 2))
+    with pytest.raises(ValueError, match="T must be"):
+        ops.sample(fake(8, 2), pf, torch.zeros(308), 0, x0=fake(8, 2))
 
 
 def test_shard_range_partitions(built_lib):
