@@ -21,7 +21,7 @@ ABI_VERSION = 2
 OK_FP32_REROUTE = 1
 
 EXPORTS = [
-    "bsdfdiff_abi_version", "bsdfdiff_error_string", "bsdfdiff_last_cuda_error", "bsdfdiff_debug_timeout_flag",
+    "bsdfdiff_abi_version", "bsdfdiff_error_string", "bsdfdiff_last_cuda_error", "bsdfdiff_debug_timeout_flag", "bsdfdiff_debug_trace",
     "bsdfdiff_device_info",
     "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_fixup_scratch_bytes",
     "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_base_log_prob", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
@@ -41,6 +41,8 @@ def _load() -> ctypes.CDLL:
     lib.bsdfdiff_error_string.restype = _c.c_char_p
     lib.bsdfdiff_error_string.argtypes = [_i]
     lib.bsdfdiff_last_cuda_error.restype = _i
+    lib.bsdfdiff_debug_trace.restype = _i
+    lib.bsdfdiff_debug_trace.argtypes = [_vp, _i]
     lib.bsdfdiff_device_info.argtypes = [_c.POINTER(_i)] * 3
     lib.bsdfdiff_packed_flow_bytes.restype = _c.c_size_t
     lib.bsdfdiff_packed_flow_bytes.argtypes = [_i, _i, _i]

@@ -33,6 +33,8 @@ extern "C" int bsdfdiff_last_cuda_error(void) { return g_last_cuda_error; }
 
 extern "C" int bsdfdiff_debug_timeout_flag(void) { return (int)tc_timeout_flag(); }
 
+extern "C" int bsdfdiff_debug_trace(unsigned long long* out_host, int max_words) { return tc_trace_read(out_host, max_words); }
+
 extern "C" int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail_cuda();

@@ -62,6 +62,8 @@
 // non-overlapping 144-column map (three groups) that the aliased build is checked against bit for bit.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace bsdfdiff {
 
 #ifndef BSDFDIFF_TC_GROUPS
@@ -71,8 +73,27 @@ namespace bsdfdiff {
 #define BSDFDIFF_TC_GROUPS 4      // tuning builds only: 1 or 2 groups isolate the per-round latency chain
 #endif
 #endif
-constexpr int kGroups = BSDFDIFF_TC_GROUPS;
-constexpr int kWorkerThreads = kGroups * 128;
+constexpr int kGroups = BSDFDIFF_TC_GROUPS;          // tiles in flight per CTA ("pipes"): one TMEM column block, one d_ready barrier each
+// BSDFDIFF_TC_DUO: every worker thread owns the same row of TWO tiles and alternates between them, so a tile's
+// tensor-core round trip runs under the OTHER tile's activation pass of the same thread (two worker groups x two
+// tiles instead of four groups x one tile): no warp ever sits in bar.sync or on an mbarrier with nothing to do, and
+// 12 warps at up to 168 registers replace 20 at 96.  0 = the round-1 structure (one tile per thread), kept for A/B builds.
+#ifndef BSDFDIFF_TC_DUO
+#define BSDFDIFF_TC_DUO 0        // measured (profiles/r2b_variants.txt): 4.5-5.5 ms against 3.05 ms for 16.7 M disk queries -- two
+#endif                           // worker warps per scheduler cannot cover the activation math's own latencies; tuning build only
+constexpr bool kDuo = BSDFDIFF_TC_DUO != 0;
+static_assert(!kDuo || kGroups == 4, "duo workers: two groups x two tiles");
+constexpr int kWGroups = kDuo ? kGroups / 2 : kGroups;   // worker thread groups (128 threads each)
+// who issues a tile's MMAs once its 128 rows are stored (duo only): 2 = the warp that arrives LAST (shared-memory
+// arrival counter; nobody waits for anybody), 1 = a rotating warp waits in bar.sync while the others bar.arrive and
+// move on, 0 = all four warps bar.sync (round-1 behaviour)
+#ifndef BSDFDIFF_TC_ISSUE
+#define BSDFDIFF_TC_ISSUE 2
+#endif
+#ifndef BSDFDIFF_TC_SKEW
+#define BSDFDIFF_TC_SKEW 2       // turns by which a thread's second tile trails its first (so their short output passes do not meet)
+#endif
+constexpr int kWorkerThreads = kWGroups * 128;
 constexpr int kProducerWarps = 4;                  // one 128-thread producer group: thread <-> query row of a tile
 constexpr int kTcThreads = kWorkerThreads + 32 * kProducerWarps;
 #ifndef BSDFDIFF_TC_SLOTS
@@ -127,6 +148,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ unsigned int g_tc_timeout_flag = 0;
+
+// BSDFDIFF_TC_TRACE (tuning builds): lane 0 of every warp of CTA 0 stamps %clock64 at fixed points of its rounds
+// kTraceFirst .. kTraceFirst + kTraceRounds - 1 (steady state); read back with bsdfdiff_debug_trace and analysed by
+// profiles/trace_timeline.py.  Events: 0 woke from the MMA wait, 1 first half loaded, 2 first half computed + stored,
+// 3 second half computed + stored, 4 stores landed (wait::st), 5 left the group barrier, 6 MMAs issued (issuer warp)
+constexpr int kTraceRounds = 96, kTraceFirst = 160, kTraceEvents = 8, kTraceWarps = 24;
+#ifdef BSDFDIFF_TC_TRACE
+__device__ unsigned long long g_tc_trace[kTraceWarps][kTraceRounds][kTraceEvents];
+#define TC_TRACE(ev)                                                                                          \
+    do {                                                                                                      \
+        if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && trace_r >= kTraceFirst && trace_r < kTraceFirst + kTraceRounds) \
+            g_tc_trace[threadIdx.x >> 5][trace_r - kTraceFirst][ev] = clock64();                              \
+    } while (0)
+#else
+#define TC_TRACE(ev) do { } while (0)
+#endif
 
 // Wait for the phase with the given parity.  try_wait suspends the warp in hardware instead of spinning, but it
 // also wakes on unrelated mbarrier traffic of the CTA; BACKOFF_NS > 0 (the producer, which runs a whole tile ahead)
@@ -454,6 +491,7 @@ __device__ __forceinline__ void flag_for_fixup(const FlowParams& P, bool flag, l
 
 struct TcSmem {
     unsigned long long d_ready[kGroups];
+    unsigned int arrive[kGroups];             // duo, issue mode 2: warps that have stored their rows of the pipe's current round
     unsigned long long w_bar;
     unsigned long long full[kSlots];          // producer -> worker group: the slot's records are written
     unsigned long long empty[kSlots];         // worker group -> producer: the slot has been read
@@ -496,8 +534,10 @@ __device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, 
     for (int j = 0; j < 16; j += 2) {
         float z0, z1;
         upk2(z[j >> 1], z0, z1);
-        const float h0 = z0 * __fdividef(1.0f, 1.0f + __expf(-z0));
-        const float h1 = z1 * __fdividef(1.0f, 1.0f + __expf(-z1));
+        // silu(z) = z/2 + z/2 tanh(z/2): one MUFU op per neuron (the exp form needs ex2 + rcp)
+        const float zh0 = 0.5f * z0, zh1 = 0.5f * z1;
+        const float h0 = fmaf(zh0, tanh_approx(zh0), zh0);
+        const float h1 = fmaf(zh1, tanh_approx(zh1), zh1);
         const float4 w0 = reinterpret_cast<const float4*>(S.bwot)[j], w1 = reinterpret_cast<const float4*>(S.bwot)[j + 1];
         const f32x2 hh0 = pk2(h0, h0), hh1 = pk2(h1, h1);
         p01 = fma2(hh0, pk2(w0.x, w0.y), p01); p23 = fma2(hh0, pk2(w0.z, w0.w), p23);
@@ -590,15 +630,146 @@ __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint6
 // before one elected lane issues the round.
 template <bool TANGENTS, int H>
 __device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH, uint32_t tg_mma, uint64_t b_hid0,
-                                                  uint64_t b_out, uint64_t av_desc, uint32_t bar) {
+                                                  uint64_t b_out, uint64_t av_desc, uint32_t bar, int trace_r = 0) {
     if (kSmemAv && TANGENTS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared operands -> tensor core
     tc_wait_st();
     tc_fence_before();
+    TC_TRACE(4);
     group_sync(g);
+    TC_TRACE(5);
     if (q == 0) {
         if (elect_one()) { tc_fence_after(); issue_round<TANGENTS, H>(type, NH, tg_mma, b_hid0, b_out, av_desc, bar); }
+        TC_TRACE(6);
     }
 }
+
+// First-layer operand of one Euler step for this thread's row: A1 (over A_h) = state hi/lo parts in columns 0..3, PE5(wi)
+// from the tile's shared-memory record in 4..14, zero in 15; tangent seeds d(input row)/d(state) -> A_u, A_v (K chunk 0).
+template <int DOMAIN, bool TANGENTS, int H>
+__device__ __forceinline__ void build_first_operand(const float (*f)[kTile], int row, float x0, float x1, float alpha,
+                                                    uint32_t tg, uint32_t av_row) {
+    uint32_t a1[16];
+#pragma unroll
+    for (int j = 0; j < 11; ++j) a1[4 + j] = __float_as_uint(f[kFPe + j][row]);
+    a1[15] = 0u;
+    float s0, s1, s2v, s3;
+    if (DOMAIN == kDisk) { s0 = x0; s1 = x1; s2v = alpha; s3 = 0.0f; }
+    else { __sincosf(x1, &s1, &s2v); s0 = x0; s3 = alpha; }
+    const uint32_t c01 = pack_h2(s0, s1), c23 = pack_h2(s2v, s3);
+    const uint32_t l01 = pack_h2(s0 - h2_lo(c01), s1 - h2_hi(c01));
+    const uint32_t l23 = pack_h2(s2v - h2_lo(c23), s3 - h2_hi(c23));
+    uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // d/dx0 (d/dtheta): k = 0
+    uint32_t ev[8] = {0x3C000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // disk d/dx1: k = 1
+    if (DOMAIN == kDisk) {
+        // k: x0_hi x1_hi | a_hi a_lo | x0_lo x1_lo | 0 0
+        a1[0] = c01; a1[1] = (c23 & 0xffffu) | (l23 << 16); a1[2] = l01; a1[3] = 0u;
+    } else {
+        // k: th_hi sin_hi | cos_hi a_hi | th_lo sin_lo | cos_lo a_lo
+        a1[0] = c01; a1[1] = c23; a1[2] = l01; a1[3] = l23;
+        // d/dphi: d(sin) = cos on k = 1, d(cos) = -sin on k = 2 (hi parts), lo parts on k = 5, 6 (the
+        // weight image repeats W1[:,1], W1[:,2] there)
+        ev[0] = c23 << 16; ev[1] = (c01 >> 16) ^ 0x8000u; ev[2] = l23 << 16; ev[3] = (l01 >> 16) ^ 0x8000u;
+    }
+    tmem_st8(tg + col_ah<H>(), a1);
+    tmem_st8(tg + col_ah<H>() + 8, a1 + 8);
+    if (TANGENTS) {
+        tmem_st8(tg + kColAu, eu);
+        if (kSmemAv) smem_st_a16(av_row, 0, ev); else tmem_st8(tg + kColAv, ev);
+    }
+}
+
+// One activation pass over this thread's row of a tile whose round has completed: tcgen05.ld z (fp32), du, dv (packed
+// fp16) -> h = silu(z), u = s2 du, v = s2 dv -> fp16 operand words of the next round (tcgen05.st).  The second half of the
+// accumulators streams in under the first half's math.
+template <bool TANGENTS, int ACT, int H>
+__device__ __forceinline__ void activation_pass(uint32_t tg, uint32_t av_row, int trace_r = 0) {
+    if (H != 32) {
+        // wide forward-only round: H / 16 chunks of 16 neurons, the next chunk's load in flight
+        float zc[2][16];
+        uint32_t ph[8];
+        tmem_ld16(tg + kColDz, zc[0]);
+#pragma unroll
+        for (int c = 0; c < H / 16; ++c) {
+            tc_wait_ld();
+            if (c + 1 < H / 16) tmem_ld16(tg + kColDz + 16 * (c + 1), zc[(c + 1) & 1]);
+            activate16<false, ACT>(zc[c & 1], nullptr, nullptr, ph, nullptr, nullptr);
+            tmem_st8(tg + col_ah<H>() + 8 * c, ph);
+        }
+        return;
+    }
+    float za[16], zb[16];
+    uint32_t ua[TANGENTS ? 8 : 1], va[TANGENTS ? 8 : 1], ub[TANGENTS ? 8 : 1], vb[TANGENTS ? 8 : 1];
+    tmem_ld16(tg + kColDz, za);
+    if (TANGENTS) { tmem_ld8_pack16(tg + kColDu, ua); tmem_ld8_pack16(tg + kColDv, va); }
+    tc_wait_ld();
+    TC_TRACE(1);
+    tmem_ld16(tg + kColDz + 16, zb);           // second half streams in under the first half's math
+    if (TANGENTS) { tmem_ld8_pack16(tg + kColDu + 16, ub); tmem_ld8_pack16(tg + kColDv + 16, vb); }
+    uint32_t ph[8], pu[8], pv[8];
+    activate16<TANGENTS, ACT>(za, ua, va, ph, pu, pv);
+    tmem_st8(tg + col_ah<H>(), ph);
+    if (TANGENTS) {
+        tmem_st8(tg + kColAu, pu);
+        if (kSmemAv) smem_st_a16(av_row, 0, pv); else tmem_st8(tg + kColAv, pv);
+    }
+    tc_wait_ld();
+    TC_TRACE(2);
+    activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
+    tmem_st8(tg + col_ah<H>() + 8, ph);
+    if (TANGENTS) {
+        tmem_st8(tg + kColAu + 8, pu);
+        if (kSmemAv) smem_st_a16(av_row, 2, pv); else tmem_st8(tg + kColAv + 8, pv);
+    }
+    TC_TRACE(3);
+}
+
+// Duo workers: hand a pipe's freshly written operands to the tensor core without making anybody wait.
+//   mode 2: every warp bumps the pipe's shared-memory arrival counter (acq_rel) after its stores have landed; the warp
+//           that observes the fourth arrival of the round issues the MMAs.  Arrivals of round r+1 can only start after
+//           round r's MMAs have completed (every warp waits on d_ready first), so the counter never mixes rounds.
+//   mode 1: a rotating warp (round number mod 4) blocks in bar.sync, the other three bar.arrive and go on.
+//   mode 0: all four warps bar.sync; the group's first warp issues.
+template <bool TANGENTS, int H>
+__device__ __forceinline__ void publish_and_issue_duo(TcSmem& S, int pipe, int q, int lane, uint32_t& rounds, int type,
+                                                      int NH, uint32_t tg_mma, uint64_t b_hid0, uint64_t b_out,
+                                                      uint32_t bar) {
+    tc_wait_st();
+    tc_fence_before();
+    bool mine;
+    if (BSDFDIFF_TC_ISSUE == 2) {
+        uint32_t old = 0;
+        __syncwarp();
+        if (lane == 0)
+            asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&S.arrive[pipe])) : "memory");
+        old = __shfl_sync(0xffffffffu, old, 0);
+        mine = (old & 3u) == 3u;
+    } else if (BSDFDIFF_TC_ISSUE == 1) {
+        mine = (int)(rounds & 3u) == q;
+        if (mine) asm volatile("bar.sync %0, %1;" ::"r"(pipe + 1), "r"(128) : "memory");
+        else asm volatile("bar.arrive %0, %1;" ::"r"(pipe + 1), "r"(128) : "memory");
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(pipe + 1), "r"(128) : "memory");
+        mine = (q == 0);
+    }
+    ++rounds;
+    if (mine) {
+        if (elect_one()) { tc_fence_after(); issue_round<TANGENTS, H>(type, NH, tg_mma, b_hid0, b_out, 0ull, bar); }
+    }
+}
+
+// Per-thread state of one of the two tiles a duo worker thread owns.
+struct Pipe {
+    float x0, x1, R, p0, theta_o;
+    CondTrack cond;
+    long long k;            // index of the tile in this CTA's tile list (k % kGroups == pipe)
+    int sl;                 // ring slot of tile k
+    uint32_t use;           // ring lap of tile k
+    uint32_t pd;            // phase parity of the pipe's d_ready barrier
+    uint32_t rounds;        // rounds published so far (issue mode 1)
+    int t;                  // Euler step
+    int phase;              // -1: take the next tile; 0..NH-1: activation pass of that round; NH: output pass
+    bool alive;
+};
 
 // Raw per-query inputs of one tile row, loaded one tile ahead by the producer so the global-load latency is
 // never on anybody's critical path.
@@ -654,7 +825,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
     // ---- one-time setup ---------------------------------------------------------------------------
     if (threadIdx.x == 0) {
-        for (int g = 0; g < kGroups; ++g) mbar_init(smem_u32(&S.d_ready[g]), 1);
+        for (int g = 0; g < kGroups; ++g) { mbar_init(smem_u32(&S.d_ready[g]), 1); S.arrive[g] = 0u; }
         for (int sl = 0; sl < kSlots; ++sl) {
             mbar_init(smem_u32(&S.full[sl]), kProducerWarps);      // one arrival per producer warp
             mbar_init(smem_u32(&S.empty[sl]), 4);                  // one arrival per warp of the consuming group
@@ -691,9 +862,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     // tile list of this CTA: blockIdx.x, +gridDim.x, ...; entry k goes to group k % kGroups through slot k % kSlots
     const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp >= kGroups * 4) {
+    if (warp >= kWGroups * 4) {
         // =========================== producer ==========================================================
-        const int row = (warp - kGroups * 4) * 32 + lane;
+        const int row = (warp - kWGroups * 4) * 32 + lane;
         RawIn cur, nxt;
         cur.wa = cur.wb = cur.wc = cur.oa = cur.ob = cur.oc = cur.r0 = cur.r1 = 0.0f;
         nxt = cur;
@@ -749,8 +920,126 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             cur = nxt; i = i_n; valid = valid_n;
             if (++sl == kSlots) { sl = 0; ++use; }
         }
+    } else if (kDuo) {
+        // =========================== workers, two tiles per thread ====================================
+        const int g = warp >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t w_base = smem_u32(S.w16);
+        const uint64_t b_hid0 = make_b_desc(w_base, H * 16, 128);                // first / hidden layers: N = H rows
+        uint64_t b_out = make_b_desc(w_base + 2u * H * 32u * 2u + (uint32_t)(NH - 1) * (2u * H * H * 2u), 256, 128);   // N = 16
+        asm volatile("" : "+l"(b_out));
+        const float inv_t = (float)(1.0 / (double)P.T);
+        const float step = (MODE == kModePdf) ? -inv_t : inv_t;
+        mbar_wait(smem_u32(&S.w_bar), 0);                                       // weights have landed in smem (any warp may issue)
+
+        // one turn of tile slot SLOT (0 | 1) of this thread: pipe = g + 2 SLOT (both groups get a tile before either gets two)
+        auto turn = [&](auto slot_tag, Pipe& p) {
+            constexpr int SLOT = decltype(slot_tag)::value;
+            const int pipe = g + kWGroups * SLOT;
+            const uint32_t tg_mma = tmem_base + pipe * kColsPerGroup;            // lane field 0: MMA operand addresses
+            const uint32_t tg = tg_mma + ((uint32_t)(q * 32) << 16);             // this warp's 32-lane window
+            const uint32_t bar_d = smem_u32(&S.d_ready[pipe]);
+            bool build = false;
+            if (p.phase >= 0) {
+                mbar_wait(bar_d, p.pd); p.pd ^= 1u;
+                tc_fence_after();
+                if (p.phase < NH) {
+                    // ---- activation pass of round `phase`; the next round goes to the tensor core ----
+                    activation_pass<TANGENTS, ACT, H>(tg, 0u);
+                    publish_and_issue_duo<TANGENTS, H>(S, pipe, q, lane, p.rounds, p.phase + 1, NH, tg_mma, b_hid0, b_out, bar_d);
+                    ++p.phase;
+                    return;
+                }
+                // ---- output pass: d, dd/dx0, dd/dx1 -> determinant, Euler update ----
+                float d0, d1, du0 = 0.f, du1 = 0.f, dv0 = 0.f, dv1 = 0.f;
+                tmem_ld2(tg + kColDz, d0, d1);
+                if (TANGENTS) { tmem_ld2(tg + kColDu, du0, du1); tmem_ld2(tg + kColDv, dv0, dv1); }
+                tc_wait_ld();
+                if (TANGENTS) {
+                    const float j00 = fmaf(step, du0, 1.0f), j01 = step * dv0;
+                    const float j10 = step * du1, j11 = fmaf(step, dv1, 1.0f);
+                    const float det = j00 * j11 - j01 * j10;
+                    p.R = (MODE == kModePdf) ? p.R * det : __fdividef(p.R, det);
+                    p.cond.step(j00, j01, j10, j11, det);
+                }
+                p.x0 = fmaf(step, d0, p.x0);
+                p.x1 = fmaf(step, d1, p.x1);
+                if (++p.t < P.T) {
+                    build = true;
+                } else {
+                    // ---- tile done: epilogue, hand the ring slot back, move to this pipe's next tile ----
+                    const long long i_raw = (blockIdx.x + p.k * gridDim.x) * kTile + row;
+                    const bool valid = i_raw < P.n;
+                    const long long i = valid ? i_raw : (P.n - 1);
+                    const float (*f)[kTile] = S.slot[p.sl];
+                    if (MODE == kModeSample) {
+                        if (valid) store_sample<true>(P, i, p.x0, p.x1, p.p0 * p.R);
+                        if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && p.cond.weight() < P.fix_thr, i);
+                    } else if (MODE == kModePdf) {
+                        float bp[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bp[j] = f[kFBp + j][row];
+                        const float wiz = f[kFWiz][row], wox = f[kFWo][row], woy = f[kFWo + 1][row], woz = f[kFWo + 2][row];
+                        if (valid)
+                            store_pdf<true>(P, i, __expf(base_logprob_fast<DOMAIN>(bp, p.x0, p.x1)) * p.R, wiz, wox, woy, woz,
+                                            p.theta_o);
+                        if (P.fix_thr > 0.0f) {
+                            const float kappa = (DOMAIN == kDisk) ? 0.0f : softplus_fast(bp[3]) + 1e-3f;
+                            const float gn = base_grad_norm(DOMAIN, bp, kappa, p.x0, p.x1);
+                            flag_for_fixup(P, valid && p.cond.weight() * fminf(1.0f, __fdividef(25.0f, gn)) < P.fix_thr, i);
+                        }
+                    } else {
+                        if (valid) reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(p.x0, p.x1);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&S.empty[p.sl]));        // every read of the record is done
+                    p.k += kGroups;
+                    p.sl += kGroups;
+                    if (p.sl >= kSlots) { p.sl -= kSlots; ++p.use; }
+                    p.phase = -1;
+                    p.alive = p.k < my_tiles;
+                    if (!p.alive) return;
+                }
+            }
+            if (p.phase < 0) {
+                // ---- take this row's record of the pipe's next tile from the producer ----
+                mbar_wait(smem_u32(&S.full[p.sl]), p.use & 1u);
+                const float (*f)[kTile] = S.slot[p.sl];
+                p.x0 = f[kFX][row]; p.x1 = f[kFX + 1][row];
+                p.p0 = (MODE == kModeSample) ? f[kFP0][row] : 1.0f;
+                p.theta_o = p.x0;
+                p.R = 1.0f;
+                p.cond.reset();
+                p.t = 0;
+                build = true;
+            }
+            if (build) {
+                // ---- first-layer operand of step t, round 0 to the tensor core ----
+                const float tf = (float)p.t / (float)P.T;
+                const float alpha = (MODE == kModePdf) ? 1.0f - tf : tf;
+                build_first_operand<DOMAIN, TANGENTS, H>(S.slot[p.sl], row, p.x0, p.x1, alpha, tg, 0u);
+                publish_and_issue_duo<TANGENTS, H>(S, pipe, q, lane, p.rounds, 0, NH, tg_mma, b_hid0, b_out, bar_d);
+                p.phase = 0;
+            }
+        };
+
+        Pipe pa, pb;
+        pa.k = g;            pa.sl = g;            pa.alive = pa.k < my_tiles;
+        pb.k = g + kWGroups; pb.sl = g + kWGroups; pb.alive = pb.k < my_tiles;
+        pa.use = pb.use = 0u; pa.pd = pb.pd = 0u; pa.rounds = pb.rounds = 0u; pa.phase = pb.phase = -1; pa.t = pb.t = 0;
+        pa.x0 = pa.x1 = pb.x0 = pb.x1 = 0.0f; pa.R = pb.R = pa.p0 = pb.p0 = 1.0f; pa.theta_o = pb.theta_o = 0.0f;
+        pa.cond.reset(); pb.cond.reset();
+        int skew = BSDFDIFF_TC_SKEW;
+#pragma unroll 1
+        while (pa.alive || pb.alive) {
+            if (pa.alive) turn(std::integral_constant<int, 0>{}, pa);
+            if (pb.alive) {
+                if (skew > 0 && pa.alive) --skew;
+                else turn(std::integral_constant<int, 1>{}, pb);
+            }
+        }
     } else {
-        // =========================== workers ===========================================================
+        // =========================== workers, one tile per thread (round-1 structure; A/B and NOALIAS builds) ==========
         const int g = warp >> 2, q = warp & 3;
         const int row = q * 32 + lane;
         const uint32_t tg_mma = tmem_base + g * kColsPerGroup;                   // lane field 0: MMA operand addresses
@@ -768,6 +1057,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         const float inv_t = (float)(1.0 / (double)P.T);
         const float step = (MODE == kModePdf) ? -inv_t : inv_t;
         if (q == 0) mbar_wait(smem_u32(&S.w_bar), 0);                           // weights have landed in smem
+        int trace_r = 0;
+        (void)trace_r;
 
 #pragma unroll 1
         for (long long k = g; k < my_tiles; k += kGroups) {
@@ -789,41 +1080,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             for (int t = 0; t < P.T; ++t) {
                 const float tf = (float)t / (float)P.T;
                 const float alpha = (MODE == kModePdf) ? 1.0f - tf : tf;
-                // ---- first-layer operand A1 (over A_h): state hi/lo parts in columns 0..3, PE5(wi) from the record in
-                //      4..15; tangent seeds -> A_u, A_v chunk 0 ----
-                {
-                    uint32_t a1[16];
-#pragma unroll
-                    for (int j = 0; j < 11; ++j) a1[4 + j] = __float_as_uint(f[kFPe + j][row]);
-                    a1[15] = 0u;
-                    if (MODE != kModePdf && t == P.T - 1) {      // last read of the record: hand the slot back
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
-                    }
-                    float s0, s1, s2v, s3;
-                    if (DOMAIN == kDisk) { s0 = x0; s1 = x1; s2v = alpha; s3 = 0.0f; }
-                    else { __sincosf(x1, &s1, &s2v); s0 = x0; s3 = alpha; }
-                    const uint32_t c01 = pack_h2(s0, s1), c23 = pack_h2(s2v, s3);
-                    const uint32_t l01 = pack_h2(s0 - h2_lo(c01), s1 - h2_hi(c01));
-                    const uint32_t l23 = pack_h2(s2v - h2_lo(c23), s3 - h2_hi(c23));
-                    uint32_t eu[8] = {0x00003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // d/dx0 (d/dtheta): k = 0
-                    uint32_t ev[8] = {0x3C000000u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // disk d/dx1: k = 1
-                    if (DOMAIN == kDisk) {
-                        // k: x0_hi x1_hi | a_hi a_lo | x0_lo x1_lo | 0 0
-                        a1[0] = c01; a1[1] = (c23 & 0xffffu) | (l23 << 16); a1[2] = l01; a1[3] = 0u;
-                    } else {
-                        // k: th_hi sin_hi | cos_hi a_hi | th_lo sin_lo | cos_lo a_lo
-                        a1[0] = c01; a1[1] = c23; a1[2] = l01; a1[3] = l23;
-                        // d/dphi: d(sin) = cos on k = 1, d(cos) = -sin on k = 2 (hi parts), lo parts on k = 5, 6 (the
-                        // weight image repeats W1[:,1], W1[:,2] there)
-                        ev[0] = c23 << 16; ev[1] = (c01 >> 16) ^ 0x8000u; ev[2] = l23 << 16; ev[3] = (l01 >> 16) ^ 0x8000u;
-                    }
-                    tmem_st8(tg + col_ah<H>(), a1);
-                    tmem_st8(tg + col_ah<H>() + 8, a1 + 8);
-                    if (TANGENTS) {
-                        tmem_st8(tg + kColAu, eu);
-                        if (kSmemAv) smem_st_a16(av_row, 0, ev); else tmem_st8(tg + kColAv, ev);
-                    }
+                // ---- first-layer operand A1 (over A_h) and the tangent seeds (A_u, A_v chunk 0) ----
+                build_first_operand<DOMAIN, TANGENTS, H>(f, row, x0, x1, alpha, tg, av_row);
+                if (MODE != kModePdf && t == P.T - 1) {      // last read of the record: hand the slot back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
                 }
                 publish_and_issue<TANGENTS, H>(g, q, 0, NH, tg_mma, b_hid0, b_out, av_desc, bar_d);
 
@@ -832,43 +1093,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 for (int l = 0; l < NH; ++l) {
                     mbar_wait(bar_d, pd); pd ^= 1u;
                     tc_fence_after();
-                    if (H != 32) {
-                        // wide forward-only round: H / 16 chunks of 16 neurons, the next chunk's load in flight
-                        float zc[2][16];
-                        uint32_t ph[8];
-                        tmem_ld16(tg + kColDz, zc[0]);
-#pragma unroll
-                        for (int c = 0; c < H / 16; ++c) {
-                            tc_wait_ld();
-                            if (c + 1 < H / 16) tmem_ld16(tg + kColDz + 16 * (c + 1), zc[(c + 1) & 1]);
-                            activate16<false, ACT>(zc[c & 1], nullptr, nullptr, ph, nullptr, nullptr);
-                            tmem_st8(tg + col_ah<H>() + 8 * c, ph);
-                        }
-                        publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, av_desc, bar_d);
-                        continue;
-                    }
-                    float za[16], zb[16];
-                    uint32_t ua[TANGENTS ? 8 : 1], va[TANGENTS ? 8 : 1], ub[TANGENTS ? 8 : 1], vb[TANGENTS ? 8 : 1];
-                    tmem_ld16(tg + kColDz, za);
-                    if (TANGENTS) { tmem_ld8_pack16(tg + kColDu, ua); tmem_ld8_pack16(tg + kColDv, va); }
-                    tc_wait_ld();
-                    tmem_ld16(tg + kColDz + 16, zb);           // second half streams in under the first half's math
-                    if (TANGENTS) { tmem_ld8_pack16(tg + kColDu + 16, ub); tmem_ld8_pack16(tg + kColDv + 16, vb); }
-                    uint32_t ph[8], pu[8], pv[8];
-                    activate16<TANGENTS, ACT>(za, ua, va, ph, pu, pv);
-                    tmem_st8(tg + col_ah<H>(), ph);
-                    if (TANGENTS) {
-                        tmem_st8(tg + kColAu, pu);
-                        if (kSmemAv) smem_st_a16(av_row, 0, pv); else tmem_st8(tg + kColAv, pv);
-                    }
-                    tc_wait_ld();
-                    activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
-                    tmem_st8(tg + col_ah<H>() + 8, ph);
-                    if (TANGENTS) {
-                        tmem_st8(tg + kColAu + 8, pu);
-                        if (kSmemAv) smem_st_a16(av_row, 2, pv); else tmem_st8(tg + kColAv + 8, pv);
-                    }
-                    publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, av_desc, bar_d);
+                    TC_TRACE(0);
+                    activation_pass<TANGENTS, ACT, H>(tg, av_row, trace_r);
+                    publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, av_desc, bar_d, trace_r);
+#ifdef BSDFDIFF_TC_TRACE
+                    ++trace_r;
+#endif
                 }
 
                 // ---- output round: d, dd/dx0, dd/dx1 ----
@@ -968,6 +1198,18 @@ int launch_tc(const FlowParams& P, cudaStream_t stream, int variant) {
     if (P.domain == kDisk)
         return variant == 2 ? launch_tc_m<kDisk, 0>(P, stream) : launch_tc_m<kDisk, 1>(P, stream);
     return variant == 2 ? launch_tc_m<kSpherical, 0>(P, stream) : launch_tc_m<kSpherical, 1>(P, stream);
+}
+
+int tc_trace_read(unsigned long long* out, int max_words) {
+#ifdef BSDFDIFF_TC_TRACE
+    const int words = kTraceWarps * kTraceRounds * kTraceEvents;
+    if (max_words < words) return -1;
+    if (cudaMemcpyFromSymbol(out, g_tc_trace, sizeof(unsigned long long) * words) != cudaSuccess) return -3;
+    return words;
+#else
+    (void)out; (void)max_words;
+    return 0;
+#endif
 }
 
 unsigned int tc_timeout_flag() {

@@ -219,7 +219,8 @@ class MultiMaterialSampler:
                 s = self.samplers[m]
                 ops.sample_into(wi_s[a:a + c], s.flow, s.base, s.T, wo_s[a:a + c], pdf_s[a:a + c],
                                 epilogue=s.epilogue, x0=None if x0_s is None else x0_s[a:a + c], seed=seed,
-                                offset=offset, first_index=first_index + a, precision=s.precision)
+                                offset=offset, first_index=first_index + a, precision=s.precision, fixup=s.fixup,
+                                scratch=torch.empty(ops.sample_scratch_elems(c), dtype=torch.int32, device=wi.device))
             a += c
         wo = torch.empty_like(wo_s)
         pdf = torch.empty_like(pdf_s)

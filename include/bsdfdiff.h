@@ -71,6 +71,9 @@ int         bsdfdiff_abi_version(void);
 const char* bsdfdiff_error_string(int code);
 int         bsdfdiff_last_cuda_error(void);          /* cudaError_t of the last failure on this thread */
 int         bsdfdiff_debug_timeout_flag(void);       /* 1 if a tensor-core kernel ever hit its mbarrier watchdog (syncs) */
+/* Tuning builds (-DBSDFDIFF_TC_TRACE) only: copies the per-warp %clock64 stamps of CTA 0's steady-state rounds to the host
+ * ([24 warps][96 rounds][8 events] uint64; see flow_tc.cu); returns the number of words, 0 in the shipped build. */
+int         bsdfdiff_debug_trace(unsigned long long* out_host, int max_words);
 
 /* ---- weight packing (host side; the blob is then copied to the device by the caller) ------------------------
  * Flow net = bias-free MLP, layers given as row-major [rows,cols] fp32 matrices exactly as the checkpoints
