@@ -2,20 +2,29 @@
 """bench.py -- headline benchmark of the fused neural-BSDF sampler (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload disk|spherical] [--queries Q] [--precision tc16|fp32]
+                    [--workload disk|spherical] [--mode sample|pdf] [--queries Q] [--precision tc16|fp32]
+                    [--no-e2e] [--no-cpu] [--no-extra]
 
-A "step" is one pass of the hot path (fused sample + pdf) over one batch of synthetic queries:
-N=1 workload = BASELINE.json configs[1], "measured BRDF disk-domain sampler: 16M (wi, noise) queries,
-full diffusion steps (T=4, the plugin's setting), 1 GPU"; for N>1 every rank gets its own 16M-query shard
-(weak scaling, no collective on the data path; Philox counters are global row indices).
-Prints ONE JSON line (rank 0).  ``value`` = whole-job samples/s with inputs resident in HBM;
-``e2e`` = the same metric through the plugin-level host-buffer call (pinned host wi in, wo+pdf out,
-copies inside the timed region); ``roofline`` = achieved algorithmic TFLOP/s of the fused kernel vs
-the measured dense-fp16/bf16 tensor peak; ``cpu_baseline`` = the CPU oracle port on the host cores.
+A "step" is one pass of the hot path over one batch of synthetic queries.  Headline (N=1) = BASELINE.json
+configs[1], "measured BRDF disk-domain sampler: 16M (wi, noise) queries, full diffusion steps (T=4, the plugin's
+setting), 1 GPU", mode sample (= the fused sample+pdf kernel; the pdf is a by-product of the same launch); for N>1
+every rank gets its own 16M-query shard (weak scaling, no collective on the data path; Philox counters are global
+row indices).  The shipped product path is timed: the tcgen05 kernel PLUS its conditioning-triggered fp32 fix-up
+launch.  Prints ONE JSON line (rank 0):
+  value        whole-job samples/s, inputs resident in HBM, CUDA events, max over ranks
+  roofline     achieved algorithmic TFLOP/s of the launch pair vs the measured dense-fp16/bf16 tensor peak;
+               traffic = DRAM bytes per launch read from the committed ncu summary under profiles/
+  e2e          the same metric through plugins.NeuralBSDFSampler.sample_host (pinned host wi in, wo+pdf out, copies
+               inside the timed region) + the copy-only ceiling of the same pipeline (kernels skipped)
+  extra        the other BASELINE configs as short lines: configs[2] (spherical, T=8: sample, then pdf() of the produced
+               wo) and disk pdf()
+  cpu_baseline the reference's own PyTorch code (oracle/_ref, built by oracle/make_ref.py) on the host cores on a bounded
+               sample, with the C/OpenMP port's figure beside it
 
-``--impl reference`` times the reference's CPU implementation of the path.  The reference is
-Python/PyTorch and cannot travel to the GPU box, so this arm runs the oracle's C/OpenMP port
-(oracle/bsdf_oracle.c, pinned against the reference's own outputs) on all host threads.
+``--impl reference`` times the reference's CPU implementation of the path on all host threads: exactly --warmup + --steps
+steps of a FIXED, stated sample of the workload (REF_QUERIES queries per step), through the reference's own
+network_sampling_* functions and nn.Modules (cpu_baseline.kind = "reference") when oracle/_ref exists, else through the
+C/OpenMP port (kind = "port").
 """
 from __future__ import annotations
 
@@ -116,28 +125,98 @@ def measured_peak():
     return 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_leg(workload, T, n_target_s=12.0):
-    """Time the CPU oracle port (C + OpenMP, all host threads) on a bounded sample of the same workload."""
-    from oracle import bsdf_oracle as O
-    from oracle import c_oracle as C
-    flow, base, _ = O.load_material_npz(os.path.join(ROOT, "tests", "golden", MATERIAL[workload] + ".npz"))
-    epi = 1 if workload == "disk" else 2
-    rng = np.random.default_rng(0)
+REF_QUERIES = 262_144          # queries per step of the CPU arms (fixed and stated; a 16.7 M-query step would take ~40 s)
 
-    def run(n_side):
-        wi3 = synth_wi3(workload, n_side, 1)
-        wi2 = wi3[:, :2] if workload == "disk" else O.cart_to_spher(wi3)
-        x0 = (O.draw_x0_disk if workload == "disk" else O.draw_x0_spherical)(base, wi2, rng)
+
+def domain_wi(workload, wi3):
+    """plugin-frame wi [n,3] -> the [n,2] conditioning the reference's sampler functions take
+    (brdf_measured_disk.py:66-67 / brdf_measured_spherical.py:35-39,76-77)."""
+    if workload == "disk":
+        return np.ascontiguousarray(wi3[:, :2])
+    r = np.sqrt((wi3 * wi3).sum(1))
+    return np.stack([np.arccos(wi3[:, 2] / (r + 1e-8)), np.arctan2(wi3[:, 1], wi3[:, 0])], 1).astype(np.float32)
+
+
+class CpuArm:
+    """The reference's CPU implementation of the path, fixed sample per step.  kind "reference" = the reference's own
+    PyTorch functions/modules/checkpoints from oracle/_ref; kind "port" = oracle/bsdf_oracle.c (C/OpenMP)."""
+
+    def __init__(self, workload, mode, prefer_reference=True, n=REF_QUERIES):
+        self.workload, self.mode = workload, mode
+        self.T = 4 if workload == "disk" else 8
+        side = int(round(np.sqrt(n)))
+        self.n = side * side
+        self.wi3 = synth_wi3(workload, side, 1)
+        self.threads = os.cpu_count() or 1
+        os.environ["OMP_NUM_THREADS"] = str(self.threads)       # torchrun pins it to 1 for every rank
+        self.kind = "port"
+        if prefer_reference:
+            try:
+                from oracle import make_ref
+                fns = make_ref.load(workload)
+            except Exception:                                    # noqa: BLE001
+                fns = None
+            if fns is not None:
+                import torch
+                torch.set_num_threads(self.threads)
+                self.torch = torch
+                self.fs, self.fp = fns
+                self.wi2 = torch.from_numpy(domain_wi(workload, self.wi3))
+                self.kind = "reference"
+                torch.manual_seed(0)
+                self.wo = self.fs(self.wi2)[0].detach() if mode == "pdf" else None
+        if self.kind == "port":
+            from oracle import bsdf_oracle as O
+            from oracle import c_oracle as C
+            self.C = C
+            self.flow, self.base, _ = O.load_material_npz(os.path.join(ROOT, "tests", "golden", MATERIAL[workload] + ".npz"))
+            wi2 = domain_wi(workload, self.wi3)
+            self.x0 = (O.draw_x0_disk if workload == "disk" else O.draw_x0_spherical)(self.base, wi2, np.random.default_rng(0))
+            self.epi = 1 if workload == "disk" else 2
+            self.threads = C.num_threads()
+            self.wo3 = C.sample(self.flow, self.base, self.wi3, self.T, self.x0, epilogue=self.epi)[0] if mode == "pdf" else None
+
+    def step(self):
         t = time.perf_counter()
-        C.sample(flow, base, wi3, T, x0, epilogue=epi)
-        return wi3.shape[0], time.perf_counter() - t
+        if self.kind == "reference":
+            if self.mode == "sample":
+                self.fs(self.wi2)
+            else:
+                self.fp(self.wo, self.wi2)
+        elif self.mode == "sample":
+            self.C.sample(self.flow, self.base, self.wi3, self.T, self.x0, epilogue=self.epi)
+        else:
+            self.C.pdf(self.flow, self.base, self.wo3, self.wi3, self.T, epilogue=self.epi)
+        return time.perf_counter() - t
 
-    n, dt = run(256)                                    # 65 536 queries: calibrate
-    rate = n / dt
-    side = int(min(4096, max(256, np.sqrt(rate * n_target_s))))
-    n, dt = run(side)
-    return {"value": n / dt, "unit": "samples/s", "cores": C.num_threads(), "kind": "port",
-            "sample": f"{n} queries ({side}x{side} stratified wi, same material/T), {dt:.1f} s, C/OpenMP oracle"}, n, dt
+    def run(self, steps, warmup):
+        for _ in range(warmup):
+            self.step()
+        dts = [self.step() for _ in range(steps)]
+        return sum(dts)
+
+    def describe(self, steps, total_s):
+        what = ("the reference's network_%s_%s + nn.Modules + checkpoint (oracle/_ref), torch %d threads"
+                % ("sampling" if self.mode == "sample" else "pdf", self.workload, self.threads)) if self.kind == "reference" \
+            else "C/OpenMP port of the same algorithm (oracle/bsdf_oracle.c), %d threads" % self.threads
+        return (f"{steps} steps x {self.n} queries (stratified wi, material aniso_brushed_aluminium_1_rgb, T={self.T}, "
+                f"mode {self.mode}), {total_s:.1f} s, {what}")
+
+
+def ncu_traffic(workload, mode):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the newest committed `ncu --set full`
+    summary of this configuration under profiles/, or (None, None)."""
+    import glob
+    import re
+    tag = {"sample": "", "pdf": "_pdf"}[mode]
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r*_ncu_tc16_{workload}{tag}_summary.txt")))
+    for f in reversed(files):
+        txt = open(f).read()
+        m = re.findall(r"dram__bytes_(?:read|write)\.sum = ([0-9.]+) (\w+)", txt)
+        if len(m) >= 2:
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            return sum(float(v) * scale.get(u, 1.0) for v, u in m[:2]), os.path.relpath(f, ROOT)
+    return None, None
 
 
 def main():
@@ -147,11 +226,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="disk", choices=["disk", "spherical"])
+    ap.add_argument("--mode", default="sample", choices=["sample", "pdf"])
     ap.add_argument("--queries", type=int, default=4096 * 4096, help="queries per GPU per step")
     ap.add_argument("--precision", default=os.environ.get("BSDFDIFF_PRECISION", "tc16"), choices=["tc16", "fp32"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--cpu-port", action="store_true", help="reference arm / cpu_baseline: force the C/OpenMP port")
     args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -160,37 +243,28 @@ def main():
     F = F_DISK if args.workload == "disk" else F_SPH
     n_side = int(round(np.sqrt(args.queries)))
     n = n_side * n_side
-    config = {"workload": f"measured BRDF {args.workload}-domain sampler, fused sample+pdf, "
+    what = "fused sample+pdf" if args.mode == "sample" else "pdf() of given (wi, wo)"
+    config = {"workload": f"measured BRDF {args.workload}-domain sampler, {what}, "
                           f"{n} (wi, Philox noise) queries per GPU, T={T}, material aniso_brushed_aluminium_1_rgb",
-              "queries_per_gpu": n, "T": T, "precision": args.precision,
+              "queries_per_gpu": n, "T": T, "mode": args.mode, "precision": args.precision,
               "l2": f"inputs+outputs {n * 28 / 1e6:.0f} MB per step > 126 MB L2 (no reuse between steps)",
               "sharding": f"dp{world}: contiguous row blocks, no data-path collective"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # torchrun exports OMP_NUM_THREADS=1 for every rank; the reference arm runs on rank 0 alone and is meant
-        # to use every host thread (the OpenMP runtime reads the variable when the oracle library is first loaded)
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-        vals = []
-        for _ in range(args.warmup and 1):
-            cpu_leg(args.workload, T, 2.0)
-        last = None
-        t_tot, n_tot = 0.0, 0
-        for _ in range(max(1, min(args.steps, 3))):
-            last, nq, dt = cpu_leg(args.workload, T, 8.0)
-            t_tot += dt
-            n_tot += nq
-        v = n_tot / t_tot
-        last["value"] = v
+        arm = CpuArm(args.workload, args.mode, prefer_reference=not args.cpu_port)
+        total = arm.run(args.steps, args.warmup)
+        v = arm.n * args.steps / total
+        config["reference_sample"] = f"{arm.n} queries per step (fixed), {args.steps} timed steps after {args.warmup} warm-up steps"
+        base = {"value": v, "unit": "samples/s", "cores": arm.threads, "kind": arm.kind,
+                "sample": arm.describe(args.steps, total)}
         print(json.dumps({"impl": "reference", "metric": "BSDF samples/sec (sample+pdf)", "value": v,
                           "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                          "ms_per_step": 1e3 * t_tot / max(1, min(args.steps, 3)), "higher_is_better": True,
+                          "ms_per_step": 1e3 * total / args.steps, "queries_per_step": arm.n, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": config, "cpu_baseline": last,
-                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "note": "reference = Python/PyTorch, cannot travel to the GPU box; this arm times the "
-                                  "oracle's C/OpenMP port of the same algorithm on all host threads"}))
+                          "config": config, "cpu_baseline": base,
+                          "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
     import torch
@@ -199,74 +273,118 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    numa = pkg.sharding.bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    numa = pkg.sharding.bind_to_gpu_numa_node(local_rank)
+    config["numa_node"] = numa if numa is not None else "not exposed (single node / VM)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    layers, base = load_fixture(args.workload)
-    pf = pkg.weights.pack_flow_layers(layers, dev)
-    pb = pkg.weights.pack_base_arrays(*base, dev)
-    sampler = pkg.plugins.NeuralBSDFSampler(args.workload, pf, pb, T=T, precision=args.precision)
-    wi_np = synth_wi3(args.workload, n_side, seed=1000 + rank)
-    wi = torch.from_numpy(wi_np).to(dev)
+    fix_on = args.precision == "tc16" and pkg.ops.get_fixup_threshold() > 0
+    config["fixup_threshold"] = pkg.ops.get_fixup_threshold() if fix_on else 0.0
+    launches_per_step = 2 if fix_on else 1
     first_index = rank * n
 
-    def step(k):
-        return sampler.sample(wi, seed=2024, offset=4 * k, first_index=first_index)
+    def max_ms(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
 
-    for k in range(args.warmup):
-        out = step(k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(args.steps):
-        out = step(args.warmup + k)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    clocks.stop_flag = True
-    clocks.join(1.0)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = world * n * args.steps / (ms * 1e-3)
-    checksum = float(out[1].double().sum().item())
+    def time_device(workload, mode, steps, warmup, want_clocks=False):
+        """(ms total, queries per GPU, last output, rows the last fix-up pass recomputed, clocks) for `steps` timed steps."""
+        Tw = 4 if workload == "disk" else 8
+        layers, base = load_fixture(workload)
+        pf = pkg.weights.pack_flow_layers(layers, dev)
+        pb = pkg.weights.pack_base_arrays(*base, dev)
+        s = pkg.plugins.NeuralBSDFSampler(workload, pf, pb, T=Tw, precision=args.precision)
+        wi_np = synth_wi3(workload, n_side, seed=1000 + rank)
+        wi = torch.from_numpy(wi_np).to(dev)
+        wo = s.sample(wi, seed=7, first_index=first_index)[0] if mode == "pdf" else None
 
-    # ---- e2e: host buffers through the plugin-level call ---------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        wi_host = torch.from_numpy(wi_np).pin_memory()
-        wo_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-        pdf_host = torch.empty((n,), dtype=torch.float32).pin_memory()
-        launches_e2e = 0
-        for k in range(2):
-            sampler.sample_host(wi_host, wo_host, pdf_host, seed=2024, offset=4 * k, first_index=first_index)
+        def step(k):
+            if mode == "sample":
+                return s.sample(wi, seed=2024, offset=4 * k, first_index=first_index)
+            return s.pdf(wi, wo)
+
+        for k in range(warmup):
+            out = step(k)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        ke = max(3, min(args.steps, 10))
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
-        t0.record()
-        for k in range(ke):
-            launches_e2e += sampler.sample_host(wi_host, wo_host, pdf_host, seed=2024, offset=4 * k,
-                                                first_index=first_index)
-        t1.record()
         torch.cuda.synchronize()
-        ms_e = t0.elapsed_time(t1)
-        if world > 1:
-            t = torch.tensor([ms_e], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e = float(t.item())
+        clocks = ClockSampler(local_rank) if want_clocks else None
+        if clocks:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(steps):
+            out = step(warmup + k)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if clocks:
+            clocks.stop_flag = True
+            clocks.join(1.0)
+        fixed = pkg.ops.last_fixup_count(dev) if fix_on else 0
+        return max_ms(ms), s, wi_np, out, fixed, clocks
+
+    ms, sampler, wi_np, out, fixed_rows, clocks = time_device(args.workload, args.mode, args.steps, args.warmup, True)
+    value = world * n * args.steps / (ms * 1e-3)
+    pdf_out = out[1] if args.mode == "sample" else out
+    checksum = float(torch.nan_to_num(pdf_out.double(), nan=0.0, posinf=0.0, neginf=0.0).sum().item())
+
+    # ---- e2e: host buffers through the plugin-level call, and the copy-only ceiling of the same pipeline ----------
+    e2e = None
+    if not args.no_e2e and args.mode == "sample":
+        wi_host = torch.from_numpy(wi_np).pin_memory()
+        wo_host = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+        pdf_host = torch.empty((n,), dtype=torch.float32).pin_memory()
+        ke = max(3, min(args.steps, 10))
+
+        def host_leg(copy_only):
+            launches = 0
+            for k in range(2):
+                sampler.sample_host(wi_host, wo_host, pdf_host, seed=2024, offset=4 * k, first_index=first_index,
+                                    copy_only=copy_only)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for k in range(ke):
+                launches += sampler.sample_host(wi_host, wo_host, pdf_host, seed=2024, offset=4 * k,
+                                                first_index=first_index, copy_only=copy_only)
+            t1.record()
+            torch.cuda.synchronize()
+            return max_ms(t0.elapsed_time(t1)), launches
+
+        ms_c, _ = host_leg(True)
+        ms_e, launches_e2e = host_leg(False)
+        bytes_step = n * 28
         e2e = {"value": world * n * ke / (ms_e * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": n * 12,
-               "d2h_bytes_per_step": n * 16, "steps": ke, "ms_per_step": ms_e / ke,
-               "api": "plugins.NeuralBSDFSampler.sample_host (pinned host wi -> wo,pdf), 3-stream chunked pipeline",
-               "checksum_pdf": float(pdf_host.double().sum().item())}
+               "d2h_bytes_per_step": n * 16, "steps": ke, "ms_per_step": ms_e / ke, "gpu_launches": launches_e2e,
+               "api": "plugins.NeuralBSDFSampler.sample_host (pinned host wi -> wo,pdf), 3-stream chunked pipeline, "
+                      "slot events persistent across calls",
+               "copy_only_value": world * n * ke / (ms_c * 1e-3), "copy_only_ms_per_step": ms_c / ke,
+               "copy_only_gbs_per_gpu": bytes_step * ke / (ms_c * 1e-3) / 1e9,
+               "frac_of_copy_ceiling": ms_c / ms_e,
+               "note": "copy_only = the same chunks, streams and pinned buffers with the kernels skipped: the host<->device "
+                       "ceiling of this box at this N; e2e / ceiling says how much the kernels add on top of the copies",
+               "checksum_pdf": float(torch.nan_to_num(pdf_host.double(), nan=0.0, posinf=0.0, neginf=0.0).sum().item())}
+
+    # ---- the other BASELINE configs as short lines ---------------------------------------------------------------
+    extra = []
+    if not args.no_extra and args.precision == "tc16":
+        for wl, md in (("spherical", "sample"), ("spherical", "pdf"), ("disk", "pdf"), ("disk", "sample")):
+            if (wl, md) == (args.workload, args.mode):
+                continue
+            ks = max(3, min(args.steps, 5))
+            ms_x, _, _, _, fx, _ = time_device(wl, md, ks, 3)
+            Fx = F_DISK if wl == "disk" else F_SPH
+            qps = n * ks / (ms_x * 1e-3)
+            extra.append({"workload": wl, "mode": md, "T": 4 if wl == "disk" else 8, "value": world * qps,
+                          "unit": "samples/s", "ms_per_step": ms_x / ks, "steps": ks,
+                          "roofline_frac": qps * Fx / 1e12 / measured_peak()[0],
+                          "fixup_rows_last_step": fx})
 
     if rank != 0:
         if world > 1:
@@ -276,35 +394,41 @@ def main():
     peak, peak_src = measured_peak()
     per_gpu_qps = n * args.steps / (ms * 1e-3)
     achieved = per_gpu_qps * F / 1e12
-    # DRAM traffic of ONE launch from the committed ncu --set full capture of this exact configuration
-    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1n_ncu_tc16_disk_summary.txt); other configs: null
-    traffic = 423.12e6 if (args.workload == "disk" and n == 4096 * 4096 and args.precision == "tc16") else None
-    traffic_src = "profiles/r1n_ncu_tc16_disk_summary.txt (bytes per launch)"
-    if args.workload == "spherical" and n == 4096 * 4096 and args.precision == "tc16":
-        traffic, traffic_src = 422.80e6, "profiles/r1n_ncu_tc16_spherical_summary.txt (bytes per launch)"
+    traffic, traffic_src = ncu_traffic(args.workload, args.mode) if (n == 4096 * 4096 and args.precision == "tc16") else (None, None)
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "traffic_source": traffic_src if traffic else None, "peak_source": peak_src,
-                "kernel": "flow_tc_kernel" if args.precision == "tc16" else "flow_simt_kernel",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "kernel": ("flow_tc_kernel (+ flow_simt_kernel fix-up pass)" if fix_on else "flow_tc_kernel")
+                if args.precision == "tc16" else "flow_simt_kernel",
                 "flops_per_query": F, "avg_launch_ms": ms / args.steps,
+                "fixup_rows_last_step": fixed_rows, "fixup_share": fixed_rows / n,
                 "hbm_algorithmic_bytes_per_query": 28, "hbm_achieved_gbs": per_gpu_qps * 28 / 1e9,
                 "mufu_ceiling_frac": 0.43 if args.workload == "disk" else 0.46,
-                "note": "algorithmic FLOPs (unpadded layer shapes, value + 2 tangent columns) x queries per launch "
-                        "/ CUDA-event time per launch; per GPU. mufu_ceiling_frac = the fraction of the tensor roofline at "
-                        "which the 16 tanh/clk/SM MUFU rate saturates (one tanh per activation; DESIGN.md 4.1)"}
+                "note": "algorithmic FLOPs (unpadded layer shapes, value + 2 tangent columns) x queries per step / "
+                        "CUDA-event time per step (tensor-core launch + fix-up launch); per GPU. mufu_ceiling_frac = the "
+                        "fraction of the tensor roofline at which the 16 tanh/clk/SM MUFU rate saturates (one tanh per "
+                        "activation; DESIGN.md 4.1)"}
     line = {"metric": "BSDF samples/sec (sample+pdf)", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
             "dtype": "f16 operands / f32 accumulate+state" if args.precision == "tc16" else "f32",
             "data": "synthetic", "config": config, "roofline": roofline, "clocks": clocks.summary(),
-            "gpu_launches": args.steps * (2 if (args.precision == "tc16" and pkg.ops.get_fixup_threshold() > 0) else 1),
-            "checksum_pdf": checksum}
+            "gpu_launches": args.steps * launches_per_step, "checksum_pdf": checksum}
     if e2e:
         line["e2e"] = e2e
-    if numa is not None:
-        line["config"]["numa_node_rank0"] = numa
+    if extra:
+        line["extra"] = extra
     if not args.no_cpu and world == 1:
         try:
-            line["cpu_baseline"] = cpu_leg(args.workload, T)[0]
+            arm = CpuArm(args.workload, args.mode, prefer_reference=not args.cpu_port)
+            ks = 12 if arm.kind == "reference" else 6
+            total = arm.run(ks, 1)
+            line["cpu_baseline"] = {"value": arm.n * ks / total, "unit": "samples/s", "cores": arm.threads,
+                                    "kind": arm.kind, "sample": arm.describe(ks, total)}
+            if arm.kind == "reference":
+                port = CpuArm(args.workload, args.mode, prefer_reference=False)
+                tp = port.run(4, 1)
+                line["cpu_baseline"]["port_value"] = port.n * 4 / tp
+                line["cpu_baseline"]["port_note"] = "C/OpenMP port of the same algorithm (oracle/bsdf_oracle.c) on the same sample"
         except Exception as ex:                                      # noqa: BLE001
             line["cpu_baseline"] = {"error": repr(ex)}
     print(json.dumps(line))

@@ -428,17 +428,20 @@ __device__ __forceinline__ float log_i0_fast(float x) {
     r = fmaf(y, r, 0.1328592e-1f);  r = fmaf(y, r, 0.39894228f);
     return x - 0.5f * __logf(x) + __logf(r);
 }
+// (explicit __f*_rn intrinsics: the compiler may not contract or re-associate, so every build of this file -- the TMEM
+// map variants in particular -- evaluates the density with the same roundings)
 template <int DOMAIN>
 __device__ __forceinline__ float base_logprob_fast(const float p[4], float x0, float x1) {
     if (DOMAIN == kDisk) {
-        const float e0 = (x0 - p[0]) * __expf(-p[2]), e1 = (x1 - p[1]) * __expf(-p[3]);
-        return -kLog2Pi - (p[2] + p[3]) - 0.5f * (e0 * e0 + e1 * e1);
+        const float e0 = __fmul_rn(__fsub_rn(x0, p[0]), __expf(-p[2])), e1 = __fmul_rn(__fsub_rn(x1, p[1]), __expf(-p[3]));
+        const float q = __fmaf_rn(e0, e0, __fmul_rn(e1, e1));
+        return __fmaf_rn(-0.5f, q, __fsub_rn(-kLog2Pi, __fadd_rn(p[2], p[3])));
     }
-    const float kappa = softplus_fast(p[3]) + 1e-3f;
-    const float e = __fdividef(x0 - p[0], __expf(p[1]) + 1e-3f);
-    const float loggau = -0.5f * kLog2Pi - p[1] - 0.5f * e * e;
-    const float logvon = kappa * __cosf(x1 - p[2]) - kLog2Pi - log_i0_fast(kappa);
-    return loggau + logvon;
+    const float kappa = __fadd_rn(softplus_fast(p[3]), 1e-3f);
+    const float e = __fdividef(__fsub_rn(x0, p[0]), __fadd_rn(__expf(p[1]), 1e-3f));
+    const float loggau = __fmaf_rn(-0.5f, __fmul_rn(e, e), __fsub_rn(-0.5f * kLog2Pi, p[1]));
+    const float logvon = __fsub_rn(__fmaf_rn(kappa, __cosf(__fsub_rn(x1, p[2])), -kLog2Pi), log_i0_fast(kappa));
+    return __fadd_rn(loggau, logvon);
 }
 template <int DOMAIN>
 __device__ __forceinline__ void base_draw_fast(const float p[4], unsigned long long seed, unsigned long long offset,
@@ -956,10 +959,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 if (TANGENTS) { tmem_ld2(tg + kColDu, du0, du1); tmem_ld2(tg + kColDv, dv0, dv1); }
                 tc_wait_ld();
                 if (TANGENTS) {
-                    const float j00 = fmaf(step, du0, 1.0f), j01 = step * dv0;
-                    const float j10 = step * du1, j11 = fmaf(step, dv1, 1.0f);
-                    const float det = j00 * j11 - j01 * j10;
-                    p.R = (MODE == kModePdf) ? p.R * det : __fdividef(p.R, det);
+                    const float j00 = __fmaf_rn(step, du0, 1.0f), j01 = __fmul_rn(step, dv0);
+                    const float j10 = __fmul_rn(step, du1), j11 = __fmaf_rn(step, dv1, 1.0f);
+                    const float det = __fmaf_rn(j00, j11, -__fmul_rn(j01, j10));
+                    p.R = (MODE == kModePdf) ? __fmul_rn(p.R, det) : __fdividef(p.R, det);
                     p.cond.step(j00, j01, j10, j11, det);
                 }
                 p.x0 = fmaf(step, d0, p.x0);
@@ -1078,8 +1081,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
 #pragma unroll 1
             for (int t = 0; t < P.T; ++t) {
-                const float tf = (float)t / (float)P.T;
-                const float alpha = (MODE == kModePdf) ? 1.0f - tf : tf;
+                const float tf = __fdividef((float)t, (float)P.T);
+                const float alpha = (MODE == kModePdf) ? __fsub_rn(1.0f, tf) : tf;
                 // ---- first-layer operand A1 (over A_h) and the tangent seeds (A_u, A_v chunk 0) ----
                 build_first_operand<DOMAIN, TANGENTS, H>(f, row, x0, x1, alpha, tg, av_row);
                 if (MODE != kModePdf && t == P.T - 1) {      // last read of the record: hand the slot back
@@ -1109,10 +1112,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 if (TANGENTS) { tmem_ld2(tg + kColDu, du0, du1); tmem_ld2(tg + kColDv, dv0, dv1); }
                 tc_wait_ld();
                 if (TANGENTS) {
-                    const float j00 = fmaf(step, du0, 1.0f), j01 = step * dv0;
-                    const float j10 = step * du1, j11 = fmaf(step, dv1, 1.0f);
-                    const float det = j00 * j11 - j01 * j10;
-                    R = (MODE == kModePdf) ? R * det : __fdividef(R, det);
+                    const float j00 = __fmaf_rn(step, du0, 1.0f), j01 = __fmul_rn(step, dv0);
+                    const float j10 = __fmul_rn(step, du1), j11 = __fmaf_rn(step, dv1, 1.0f);
+                    const float det = __fmaf_rn(j00, j11, -__fmul_rn(j01, j10));
+                    R = (MODE == kModePdf) ? __fmul_rn(R, det) : __fdividef(R, det);
                     cond.step(j00, j01, j10, j11, det);
                 }
                 x0 = fmaf(step, d0, x0);
@@ -1130,7 +1133,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
                 if (valid)
-                    store_pdf<true>(P, i, __expf(base_logprob_fast<DOMAIN>(bp, x0, x1)) * R, wiz, wox, woy, woz, theta_o);
+                    store_pdf<true>(P, i, __fmul_rn(__expf(base_logprob_fast<DOMAIN>(bp, x0, x1)), R), wiz, wox, woy, woz, theta_o);
                 if (P.fix_thr > 0.0f) {
                     const float kappa = (DOMAIN == kDisk) ? 0.0f : softplus_fast(bp[3]) + 1e-3f;
                     const float gn = base_grad_norm(DOMAIN, bp, kappa, x0, x1);

@@ -596,12 +596,13 @@ def test_tmem_aliasing_build_is_bit_identical(pkg):
         assert torch.equal(out_x, ref[0]) and torch.equal(out_p, ref[1])
         wo, wie = cu(z["wo_eval"]), cu(z["wi_eval"])
         refp = pkg.ops.pdf(wo, wie, pf, pb, T, precision="tc16", fixup=0.0)
-        rc = alt.bsdfdiff_pdf(L.PREC_TC16, pf.domain, 0, T, n, wo.data_ptr(), wie.data_ptr(), pf.blob.data_ptr(),
-                              pf.hidden, pf.n_hidden, pb.data_ptr(), out_p.data_ptr(), 0.0, None,
+        out_e = torch.empty(wo.shape[0], device="cuda")
+        rc = alt.bsdfdiff_pdf(L.PREC_TC16, pf.domain, 0, T, wo.shape[0], wo.data_ptr(), wie.data_ptr(), pf.blob.data_ptr(),
+                              pf.hidden, pf.n_hidden, pb.data_ptr(), out_e.data_ptr(), 0.0, None,
                               torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         torch.cuda.synchronize()
-        assert torch.equal(out_p, refp)
+        assert torch.equal(out_e, refp)
 
 
 def test_unsupported_tensor_core_shape_reports_its_reroute(pkg):
