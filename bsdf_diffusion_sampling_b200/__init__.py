@@ -8,7 +8,7 @@ all backed by one C-ABI CUDA library (``libbsdfdiff.so``, ``include/bsdfdiff.h``
 Importing the package requires the built library; there is no CPU or PyTorch fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError if libbsdfdiff.so is missing)
-from . import ops, weights, model, mlp_brdf_sampling, reflow, plugins, sharding  # noqa: F401
+from . import ops, weights, model, mlp_brdf_sampling, reflow, measured, plugins, sharding  # noqa: F401
 from .mlp_brdf_sampling import (  # noqa: F401
     network_sampling_disk, network_sampling_disk_tiny, network_pdf_disk,
     network_sampling_spherical, network_pdf_spherical,

@@ -25,6 +25,7 @@ EXPORTS = [
     "bsdfdiff_device_info",
     "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_fixup_scratch_bytes",
     "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_base_log_prob", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
+    "bsdfdiff_measured_blob_bytes", "bsdfdiff_measured_pack", "bsdfdiff_measured_eval", "bsdfdiff_measured_weight",
 ]
 
 _c = ctypes
@@ -57,6 +58,13 @@ def _load() -> ctypes.CDLL:
     lib.bsdfdiff_flow_forward.argtypes = [_i, _i, _i, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _u64, _u64, _i64,
                                           _vp, _vp, _vp]
     lib.bsdfdiff_mlp_forward.argtypes = [_i, _i64, _vp, _i, _vp, _i, _i, _vp, _vp]
+    lib.bsdfdiff_measured_blob_bytes.restype = _c.c_size_t
+    lib.bsdfdiff_measured_blob_bytes.argtypes = [_i] * 10
+    lib.bsdfdiff_measured_pack.argtypes = [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp]
+    lib.bsdfdiff_measured_eval.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp]
+    lib.bsdfdiff_measured_weight.argtypes = [_vp, _i, _i64, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp]
+    for name in ("bsdfdiff_measured_pack", "bsdfdiff_measured_eval", "bsdfdiff_measured_weight"):
+        getattr(lib, name).restype = _i
     for name in ("bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_sample", "bsdfdiff_pdf",
                  "bsdfdiff_base_log_prob",
                  "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward", "bsdfdiff_device_info"):

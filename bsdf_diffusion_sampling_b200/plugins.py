@@ -9,9 +9,11 @@ Reference classes (all named ``MyBSDF(mi.BSDF)``):
 ``pdf(wi3, wo3) -> pdf_omega`` on torch CUDA tensors in the local shading frame, one kernel launch each;
 the domain mapping (``wi[..., :2]`` / ``cart_to_spher``), validity masks, ``disk_to_cart`` /
 ``sph_to_dir`` and the Jacobian of the domain mapping (``* cos(theta_o)`` / ``clamp(1/sin(theta_o), 1,
-FLT_MAX)``) run in the kernel epilogue instead of ~15 eager launches.  ``firefly_clamp`` is the one step
-that needs the ground-truth BSDF value and therefore stays outside the kernel
-(brdf_measured_disk.py:97-100, brdf_measured_spherical.py:106-108, bsdf_myresult.py:101-103).
+FLT_MAX)``) run in the kernel epilogue instead of ~15 eager launches.  The firefly clamp needs the
+ground-truth BSDF value (brdf_measured_disk.py:97-100, brdf_measured_spherical.py:106-108, bsdf_myresult.py:101-103): for the two
+measured plugins ``sample_weighted`` evaluates it on the GPU from the RGL tensor file (``measured.MeasuredBSDF``) and fuses
+weight, clamp and masks into one launch; ``firefly_clamp`` is the three-line torch helper for callers that bring their own
+ground-truth value (the analytic ``bsdf`` kind).
 
 ``make_mybsdf(kind)`` builds the actual ``mi.BSDF`` subclass when Mitsuba 3 + Dr.Jit are importable
 (they are not in the build container, so that glue is exercised only where Mitsuba exists); unlike the
@@ -24,6 +26,7 @@ from typing import Optional, Tuple
 
 import torch
 
+from . import measured as _measured
 from . import model, ops, weights
 
 _KINDS = {
@@ -93,6 +96,19 @@ class NeuralBSDFSampler:
         """(wi [N,3], wo [N,3]) -> pdf_omega [N] (MyBSDF.pdf incl. the cos/sin masks of the plugin kind)."""
         return ops.pdf(wo, wi, self.flow, self.base, self.T, epilogue=self.epilogue, precision=self.precision,
                        fixup=self.fixup)
+
+    def sample_weighted(self, wi: torch.Tensor, bsdf: "_measured.MeasuredBSDF", albedo=(1.0, 1.0, 1.0), *, x0=None,
+                        seed=None, offset=0, first_index=0):
+        """The whole tensor part of ``MyBSDF.sample`` of the measured plugins in two launches and no Dr.Jit <-> torch
+        round trip: the sampler kernel, then ONE kernel that evaluates the measured ground truth at the sampled
+        direction, forms ``value = brdf / bs.pdf * albedo``, applies the firefly clamp (``pdf <- 0`` where
+        ``lum(value) >= 30``) and the final masks (brdf_measured_disk.py:92-101, brdf_measured_spherical.py:100-109).
+        -> (wo [N,3], pdf_omega [N] after the clamp, weight [N,3] = what ``sample`` returns next to ``bs``)."""
+        if self.kind == "bsdf":
+            raise ValueError("the bsdf plugin kind evaluates Mitsuba's analytic models, not a measured tensor file")
+        wo, pdf = self.sample(wi, x0=x0, seed=seed, offset=offset, first_index=first_index)
+        weight, pdf = bsdf.weight_and_clamp(self.epilogue, wi, wo, pdf, albedo)
+        return wo, pdf, weight
 
     # -- host-buffer entry point (what a renderer that keeps its wavefront on the host calls) ---------
     def sample_host(self, wi_host: torch.Tensor, wo_host: torch.Tensor, pdf_host: torch.Tensor, *, seed: int,
@@ -262,8 +278,8 @@ def make_mybsdf(kind: str, checkpoint_root: str = "./checkpoints_new", bsdf_root
                 flags = mi.BSDFFlags.Diffuse | mi.BSDFFlags.FrontSide | mi.BSDFFlags.BackSide
             else:
                 material = props["filename"]
-                self.bsdf = mi.load_dict({"type": "measured",
-                                          "filename": os.path.join(bsdf_root, material + ".bsdf")})
+                # ground truth on the GPU from the same tensor file Mitsuba's `measured` plugin would load
+                self.measured = _measured.MeasuredBSDF.from_file(os.path.join(bsdf_root, material + ".bsdf"))
                 self.albedo = mi.Color3f([1, 1, 1])
                 flags = mi.BSDFFlags.DeltaReflection | mi.BSDFFlags.FrontSide
             self.sampler = NeuralBSDFSampler.from_checkpoints(kind, material, checkpoint_root)
@@ -278,29 +294,29 @@ def make_mybsdf(kind: str, checkpoint_root: str = "./checkpoints_new", bsdf_root
             bs.wo = mi.Vector3f(wo_t[:, 0], wo_t[:, 1], wo_t[:, 2])
             cos_theta_o = mi.Frame3f.cos_theta(bs.wo)
             bs.pdf = mi.Float(pdf_t)
+            if kind != "bsdf":
+                # measured kinds: weight, firefly clamp and masks in one more launch -- no Dr.Jit <-> torch round trip
+                w_t, pdf_c = self.measured.weight_and_clamp(self.sampler.epilogue, si.wi.torch(), wo_t, pdf_t,
+                                                            albedo=[float(c) for c in self.albedo])
+                bs.eta = 1.0
+                bs.sampled_type = mi.UInt32(+self.m_flags)
+                bs.sampled_component = 0
+                bs.pdf = mi.Float(pdf_c)
+                return bs, mi.Vector3f(w_t[:, 0], w_t[:, 1], w_t[:, 2]) & active
+            # bsdf kind: analytic ground truth from Mitsuba (principled / roughdielectric, rendering/bsdf_myresult.py:46,92-103)
             brdf = self.bsdf.eval(ctx, si, bs.wo)
-            if kind == "bsdf":
-                bs.sampled_component = 2
-                bs.eta = dr.select(cos_theta_o > 0.0, 1.0, 1.788)
-                bs.sampled_type = dr.select(cos_theta_o > 0.0, 8, 16)
-                value = dr.select(bs.pdf > 0.0, brdf * self.albedo / bs.pdf, mi.Vector3f(0))
-                bs.pdf = mi.Float(self.sampler.firefly_clamp(pdf_t, value.torch()))
-                return bs, dr.select(bs.pdf > 0.0, value, mi.Vector3f(0))
-            bs.eta = 1.0
-            bs.sampled_type = mi.UInt32(+self.m_flags)
-            bs.sampled_component = 0
-            value = brdf / bs.pdf * self.albedo
-            if kind == "spherical":
-                value = dr.select(active & (bs.pdf > 0.0), value, mi.Vector3f(0))
+            bs.sampled_component = 2
+            bs.eta = dr.select(cos_theta_o > 0.0, 1.0, 1.788)
+            bs.sampled_type = dr.select(cos_theta_o > 0.0, 8, 16)
+            value = dr.select(bs.pdf > 0.0, brdf * self.albedo / bs.pdf, mi.Vector3f(0))
             bs.pdf = mi.Float(self.sampler.firefly_clamp(pdf_t, value.torch()))
-            return bs, dr.select(active & (bs.pdf > 0.0) & (cos_theta_o > 0), value, mi.Vector3f(0))
+            return bs, dr.select(bs.pdf > 0.0, value, mi.Vector3f(0))
 
         def eval(self, ctx, si, wo, active=True):
-            value = self.bsdf.eval(ctx, si, wo) * self.albedo
             if kind == "bsdf":
-                return value
-            ok = (mi.Frame3f.cos_theta(si.wi) > 0.0) & (mi.Frame3f.cos_theta(wo) > 0.0)
-            return dr.select(ok, value, mi.Vector3f(0))
+                return self.bsdf.eval(ctx, si, wo) * self.albedo
+            v = self.measured.eval(si.wi.torch(), wo.torch())          # already 0 unless cos_i > 0 and cos_o > 0
+            return mi.Vector3f(v[:, 0], v[:, 1], v[:, 2]) * self.albedo
 
         def pdf(self, ctx, si, wo, active=True):
             return mi.Float(self.sampler.pdf(si.wi.torch(), wo.torch()))

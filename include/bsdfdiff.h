@@ -142,6 +142,28 @@ int bsdfdiff_flow_forward(int precision, int domain, int T, int64_t n, const flo
 int bsdfdiff_mlp_forward(int precision, int64_t n, const float* in, int in_dim, const void* flow_packed,
                          int hidden, int n_hidden, float* out /*[n,2]*/, void* cuda_stream);
 
+/* ---- measured-BSDF ground truth: Mitsuba 3 `measured` eval of an RGL tensor file, and the plugins' weight + firefly clamp ----
+ * Replaces  self.bsdf.eval(ctx, si, bs.wo)  (mi.load_dict({"type": "measured", ...}), rendering/brdf_measured_disk.py:36-42,92
+ * and rendering/brdf_measured_spherical.py:45-51,100) and the Dr.Jit<->torch round trips of the firefly clamp
+ * (brdf_measured_disk.py:93-101, brdf_measured_spherical.py:101-109).  Mitsuba is third-party and absent here: the model is
+ * implemented from its published description (Dupuy & Jakob 2018; Mitsuba 3 measured.cpp / distr_2d.h), see
+ * csrc/measured.cu and oracle/measured_oracle.py.
+ * pack (host): raw tensor-file fields, row-major as stored -- phi_i [n_phi], theta_i [n_theta], ndf [ndf_h, ndf_w],
+ * sigma [sig_h, sig_w], vndf [n_phi, n_theta, v_h, v_w], rgb [n_phi, n_theta, 3, r_h, r_w] -> blob (then copied to the device).
+ * eval:   out_rgb[n,3] = measured.eval(wi, wo) (= f cos(theta_o); 0 unless cos_i > 0 and cos_o > 0); wi, wo [n,3] local frame.
+ * weight: value = eval / bs_pdf * albedo [spherical epilogue: zeroed unless cos_i > 0 and bs_pdf > 0];
+ *         out_pdf = luminance(value) < clamp ? bs_pdf : 0;  out_weight = cos_i > 0 and out_pdf > 0 and cos_o > 0 ? value : 0.
+ *         epilogue = BSDFDIFF_EPI_DISK | BSDFDIFF_EPI_SPHERICAL (which plugin's tail); bs_pdf = the pdf bsdfdiff_sample returned. */
+size_t bsdfdiff_measured_blob_bytes(int n_phi, int n_theta, int ndf_w, int ndf_h, int sig_w, int sig_h,
+                                    int v_w, int v_h, int r_w, int r_h);
+int    bsdfdiff_measured_pack(const float* phi_i /*host*/, int n_phi, const float* theta_i, int n_theta, const float* ndf,
+                              int ndf_w, int ndf_h, const float* sigma, int sig_w, int sig_h, const float* vndf,
+                              int v_w, int v_h, const float* rgb, int r_w, int r_h, int jacobian, void* blob_out /*host*/);
+int    bsdfdiff_measured_eval(const void* blob, int64_t n, const float* wi, const float* wo, float* out_rgb, void* cuda_stream);
+int    bsdfdiff_measured_weight(const void* blob, int epilogue, int64_t n, const float* wi, const float* wo,
+                                const float* bs_pdf, float albedo_r, float albedo_g, float albedo_b, float clamp,
+                                float* out_weight, float* out_pdf, void* cuda_stream);
+
 /* Static facts about the tensor-core kernel for a given shape (for bench.py / DESIGN.md bookkeeping). */
 int bsdfdiff_device_info(int* sm_count, int* cc_major, int* cc_minor);
 

@@ -244,7 +244,7 @@ class MeasuredBSDF:
         self.ndf = Marginal2D(f["ndf"])
         self.sigma = Marginal2D(f["sigma"])
         self.vndf = Marginal2D(f["vndf"], (self.phi_i, self.theta_i), normalize=True)
-        self.luminance = Marginal2D(f["luminance"], (self.phi_i, self.theta_i), normalize=True)
+        # (the `luminance` warp only drives Mitsuba's own sample(); eval does not use it)
         self.rgb = Marginal2D(f["rgb"], (self.phi_i, self.theta_i, np.arange(3.0)))
         self.fields = f
 
