@@ -240,7 +240,18 @@ def test_fused_weight_and_firefly_clamp(built_lib, kind, net, mat):
     assert np.array_equal(got_p[ok], pdf0.cpu().numpy()[ok])
     err = np.abs(got_w - w_ref) / (np.abs(w_ref) + 1e-2)
     assert np.quantile(err[~near], 0.999) < 1e-3
-    assert 0 < (got_p == 0).mean() < 0.5                               # some lanes are clamped / masked, most are not
+    # some lanes are clamped / masked, not all.  (The measured-spherical plugin masks most lanes: it pairs the spherical flow
+    # with the *_disk* pretrain checkpoint as its base, brdf_measured_spherical.py:59 -- reference behaviour, SURVEY App. B.)
+    assert 0 < (got_p == 0).mean() < (0.5 if kind == "disk" else 0.95)
+    # the clamp decision itself, exercised with a threshold low enough to fire on a well-trained sampler too
+    thr = float(np.nanquantile(M.rgb2lum(value)[p > 0], 0.8))
+    _, p_low = m.weight_and_clamp(s.epilogue, cu(wi), wo0, pdf0, albedo, clamp=thr)
+    with np.errstate(invalid="ignore"):
+        lum = M.rgb2lum(value)
+    sure = np.abs(lum - thr) > 1e-3 * max(thr, 1.0)
+    want_zero = ~(lum < thr) | (p == 0)
+    assert ((p_low.cpu().numpy() == 0) == want_zero)[sure].all()
+    assert ((pdf0.cpu().numpy() > 0) & (p_low.cpu().numpy() == 0)).mean() > 0.02
     assert (got_w[~active] == 0).all()
 
 
