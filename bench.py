@@ -386,6 +386,72 @@ def main():
                           "roofline_frac": qps * Fx / 1e12 / measured_peak()[0],
                           "fixup_rows_last_step": fx})
 
+    # ---- twelve materials in ONE wavefront (disney_bsdf_array0_envmap.xml:35-335), single launch over
+    #      the device-built plan vs Mitsuba's per-instance dispatch (boolean-mask gather, one launch per material, scatter)
+    # ---- BASELINE configs[3]: matpreview 1920x1080 @ 64 spp through the bsdf_myresult plugin, replayed wavefront ----------
+    if not args.no_extra and args.precision == "tc16":
+        def timed(fn, steps, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return max_ms(a.elapsed_time(b)) / steps
+
+        import glob
+        mats = []
+        disk_files = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "disk_*.npz")))
+        for j in range(12):                                   # 12 table entries: the three disk fixtures, own blobs each
+            z = np.load(disk_files[j % len(disk_files)])
+            mats.append(pkg.plugins.NeuralBSDFSampler(
+                "disk", pkg.weights.pack_flow_layers([z[f"flow_w{i}"] for i in range(int(z["n_flow_layers"]))], dev),
+                pkg.weights.pack_base_arrays(z["base_w1"], z["base_b1"], z["base_wo"], z["base_bo"], dev),
+                precision=args.precision))
+        mm = pkg.plugins.MultiMaterialSampler(mats)
+        wi_m = torch.from_numpy(synth_wi3("disk", n_side, seed=77 + rank)).to(dev)
+        mid = torch.randint(0, 12, (n,), device=dev, dtype=torch.int32)
+        ms_plan = timed(lambda: mm.plan(mid), 5)
+        plan = mm.plan(mid)
+        ms_multi = timed(lambda: mm.sample(wi_m, plan=plan, seed=5, first_index=first_index), 5)
+        ms_both = timed(lambda: mm.sample(wi_m, mid, seed=5, first_index=first_index), 5)
+        ms_inst = timed(lambda: mm.sample_per_material(wi_m, mid, seed=5, first_index=first_index), 3, warm=1)
+        extra.append({"workload": "disk, 12 materials in one wavefront (random material id per row)", "mode": "sample", "T": 4,
+                      "value": world * n / (ms_both * 1e-3), "unit": "samples/s", "ms_per_step": ms_both,
+                      "ms_plan": ms_plan, "ms_kernels_given_plan": ms_multi,
+                      "ms_per_instance_dispatch": ms_inst, "roofline_frac": n / (ms_both * 1e-3) * F_DISK / 1e12 / measured_peak()[0],
+                      "note": "single launch over a device-built plan (bsdfdiff_multi_plan + bsdfdiff_sample_multi) vs the "
+                              "per-instance dispatch Mitsuba performs (mask gather + one launch per material + scatter)"})
+        del mm, mats, wi_m, mid, plan
+
+        zb = np.load(os.path.join(ROOT, "tests", "golden", "bsdf_0.npz"))
+        sb = pkg.plugins.NeuralBSDFSampler(
+            "bsdf", pkg.weights.pack_flow_layers([zb[f"flow_w{i}"] for i in range(int(zb["n_flow_layers"]))], dev),
+            pkg.weights.pack_base_arrays(zb["base_w1"], zb["base_b1"], zb["base_wo"], zb["base_bo"], dev),
+            precision=args.precision)
+        lanes, spp = 1920 * 1080, 64
+        g = torch.Generator(device=dev).manual_seed(3 + rank)
+        v = torch.randn((lanes, 3), device=dev, generator=g)
+        wi_f = v / v.norm(dim=1, keepdim=True)                # bsdf_myresult takes both hemispheres (bsdf_myresult.py:55-57)
+        wo_l = torch.randn((lanes, 3), device=dev, generator=g)
+        wo_l = wo_l / wo_l.norm(dim=1, keepdim=True)          # emitter-sampling direction of the MIS pdf() query
+
+        def one_pass(k=[0]):
+            k[0] += 1
+            sb.sample(wi_f, seed=9, offset=68 * k[0], first_index=rank * lanes)
+            sb.pdf(wi_f, wo_l)
+        ms_pass = timed(one_pass, 16)
+        extra.append({"workload": "matpreview replay: bsdf_myresult plugin (bsdf_0), 1920x1080 lanes per pass, full-sphere wi, "
+                                  "sample() + pdf() per pass, 64 spp = 64 passes per frame", "mode": "sample+pdf", "T": 8,
+                      "value": world * 2 * lanes / (ms_pass * 1e-3), "unit": "queries/s", "ms_per_pass": ms_pass,
+                      "passes_per_s": 1e3 / ms_pass, "ms_per_64spp_frame_bounce": ms_pass * spp,
+                      "roofline_frac": 2 * lanes / (ms_pass * 1e-3) * F_SPH / 1e12 / measured_peak()[0],
+                      "note": "synthetic wavefront (Mitsuba is absent): one bounce of every pixel's path per pass; the "
+                              "reference runs the same two calls as ~700 eager launches + 4 Dr.Jit<->torch crossings per pass"})
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -17,7 +17,7 @@ DISK, SPHERICAL = 0, 1
 EPI_RAW, EPI_DISK, EPI_SPHERICAL, EPI_BSDF = 0, 1, 2, 3
 PREC_FP32, PREC_TC16, PREC_TC16_EXP = 0, 1, 2
 BASE_FLOATS = 308
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK_FP32_REROUTE = 1
 
 EXPORTS = [
@@ -26,6 +26,7 @@ EXPORTS = [
     "bsdfdiff_packed_flow_bytes", "bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_fixup_scratch_bytes",
     "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_base_log_prob", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
     "bsdfdiff_measured_blob_bytes", "bsdfdiff_measured_pack", "bsdfdiff_measured_eval", "bsdfdiff_measured_weight",
+    "bsdfdiff_multi_scratch_bytes", "bsdfdiff_multi_plan", "bsdfdiff_sample_multi", "bsdfdiff_pdf_multi",
 ]
 
 _c = ctypes
@@ -63,6 +64,14 @@ def _load() -> ctypes.CDLL:
     lib.bsdfdiff_measured_pack.argtypes = [_vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _i, _i, _i, _vp]
     lib.bsdfdiff_measured_eval.argtypes = [_vp, _i64, _vp, _vp, _vp, _vp]
     lib.bsdfdiff_measured_weight.argtypes = [_vp, _i, _i64, _vp, _vp, _vp, _f, _f, _f, _f, _vp, _vp, _vp]
+    lib.bsdfdiff_multi_scratch_bytes.restype = _c.c_size_t
+    lib.bsdfdiff_multi_scratch_bytes.argtypes = [_i64, _i]
+    lib.bsdfdiff_multi_plan.argtypes = [_i64, _vp, _i, _vp, _vp]
+    lib.bsdfdiff_sample_multi.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _u64, _u64, _i64,
+                                          _vp, _vp, _vp, _f, _vp]
+    lib.bsdfdiff_pdf_multi.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _f, _vp]
+    for name in ("bsdfdiff_multi_plan", "bsdfdiff_sample_multi", "bsdfdiff_pdf_multi"):
+        getattr(lib, name).restype = _i
     for name in ("bsdfdiff_measured_pack", "bsdfdiff_measured_eval", "bsdfdiff_measured_weight"):
         getattr(lib, name).restype = _i
     for name in ("bsdfdiff_pack_flow", "bsdfdiff_pack_flow_tcnn", "bsdfdiff_sample", "bsdfdiff_pdf",

@@ -2,6 +2,7 @@
 // weight packer.  No torch types; plain pointers, sizes and a cudaStream_t passed as void*.
 #include "../../include/bsdfdiff.h"
 #include "common.cuh"
+#include "multi.cuh"
 
 #include <cstring>
 #include <vector>
@@ -328,4 +329,94 @@ extern "C" int bsdfdiff_mlp_forward(int precision, int64_t n, const float* in, i
                                      n_hidden, out, stream);
     if (rc == -3) return fail_cuda();
     return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// one wavefront, several materials (multi.cu)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t bsdfdiff_multi_scratch_bytes(int64_t n, int n_materials) { return multi_scratch_bytes(n, n_materials); }
+
+extern "C" int bsdfdiff_multi_plan(int64_t n, const int32_t* material_id, int n_materials, void* scratch, void* cuda_stream) {
+    const int rc = launch_multi_plan(n, material_id, n_materials, scratch, static_cast<cudaStream_t>(cuda_stream));
+    if (rc == -3) return fail_cuda();
+    return rc;
+}
+
+// [memset fix counts] -> sampler kernel over the plan's virtual tiles -> [fix-up pass] -> zero the inactive rows
+static int dispatch_multi(int precision, FlowParams P, int n_materials, const void* const* flows, const float* const* bases,
+                          void* plan, float thr, cudaStream_t stream) {
+    if (!plan || !flows || !bases || n_materials < 1 || n_materials > kMaxMaterials || P.n > 0x7fffffffll || P.T < 1)
+        return BSDFDIFF_EINVAL;
+    const bool tc = (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP);
+    if (!tc && precision != BSDFDIFF_PREC_FP32) return BSDFDIFF_EINVAL;
+    MultiPlanView v = multi_view(plan, P.n, n_materials);
+    P.n_materials = n_materials;
+    P.flows = reinterpret_cast<const unsigned char* const*>(flows);
+    P.bases = bases;
+    P.perm = v.perm; P.tiles = v.tiles; P.n_tiles_dev = v.n_tiles; P.seg_off = v.seg_off;
+    const bool fix = tc && thr > 0.0f;
+    if (fix) {
+        P.fix_thr = thr; P.fix_count = v.fix_count; P.fix_list = v.fix_list;
+        if (P.mode == kModeSample && !P.x0 && !P.out_x0) P.out_x0 = v.x0;     // the fix-up pass replays the base sample
+        if (cudaMemsetAsync(v.fix_count, 0, sizeof(unsigned int) * 256, stream) != cudaSuccess) return fail_cuda();
+    }
+    int rc = tc ? launch_tc(P, stream, precision) : launch_simt(P, stream);
+    int note = BSDFDIFF_OK;
+    if (tc && rc == -2) {                       // shape outside the tensor-core kernel: the fp32 kernel walks the same plan
+        FlowParams Q = P;
+        Q.fix_thr = 0.0f; Q.fix_count = nullptr; Q.fix_list = nullptr;
+        rc = launch_simt(Q, stream);
+        note = BSDFDIFF_OK_FP32_REROUTE;
+    } else if (fix && rc == 0) {
+        FlowParams Q = P;
+        Q.fix_pass = 1;
+        if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; }
+        rc = launch_simt(Q, stream);
+    }
+    if (rc == -3) return fail_cuda();
+    if (rc == -4) return BSDFDIFF_ENOTSM100;
+    if (rc) return rc;
+    rc = launch_multi_zero_inactive(P.n, n_materials, plan, P.mode == kModeSample ? P.out_dir : nullptr,
+                                    P.epilogue == kEpiRaw ? 2 : 3, P.out_pdf, stream);
+    if (rc == -3) return fail_cuda();
+    return rc ? rc : note;
+}
+
+static bool bad_domain_epilogue(int domain, int epilogue) {
+    return (domain != kDisk && domain != kSpherical) || epilogue < 0 || epilogue > 3 ||
+           (epilogue == kEpiDisk && domain != kDisk) || (epilogue >= kEpiSpherical && domain != kSpherical);
+}
+
+extern "C" int bsdfdiff_sample_multi(int precision, int domain, int epilogue, int T, int64_t n, const float* wi,
+                                     const void* plan, int n_materials, const void* const* flows_packed,
+                                     const float* const* base_params, int hidden, int n_hidden, const float* x0_replay,
+                                     uint64_t seed, uint64_t offset, int64_t first_index, float* out_dir, float* out_pdf,
+                                     float* out_x0, float fix_threshold, void* cuda_stream) {
+    if (n < 0 || T < 1 || bad_domain_epilogue(domain, epilogue)) return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    if (!wi || !out_dir || !out_pdf) return BSDFDIFF_EINVAL;
+    FlowParams P{};
+    P.domain = domain; P.mode = kModeSample; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
+    P.wi = wi; P.x0 = x0_replay; P.seed = seed; P.offset = offset; P.first_index = first_index;
+    P.out_dir = out_dir; P.out_pdf = out_pdf; P.out_x0 = out_x0;
+    int rc = fill_shape(P, nullptr, domain, hidden, n_hidden);
+    if (rc) return rc;
+    return dispatch_multi(precision, P, n_materials, flows_packed, base_params, const_cast<void*>(plan), fix_threshold,
+                          static_cast<cudaStream_t>(cuda_stream));
+}
+
+extern "C" int bsdfdiff_pdf_multi(int precision, int domain, int epilogue, int T, int64_t n, const float* wo, const float* wi,
+                                  const void* plan, int n_materials, const void* const* flows_packed,
+                                  const float* const* base_params, int hidden, int n_hidden, float* out_pdf,
+                                  float fix_threshold, void* cuda_stream) {
+    if (n < 0 || T < 1 || bad_domain_epilogue(domain, epilogue)) return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    if (!wi || !wo || !out_pdf) return BSDFDIFF_EINVAL;
+    FlowParams P{};
+    P.domain = domain; P.mode = kModePdf; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
+    P.wi = wi; P.wo = wo; P.out_pdf = out_pdf;
+    int rc = fill_shape(P, nullptr, domain, hidden, n_hidden);
+    if (rc) return rc;
+    return dispatch_multi(precision, P, n_materials, flows_packed, base_params, const_cast<void*>(plan), fix_threshold,
+                          static_cast<cudaStream_t>(cuda_stream));
 }

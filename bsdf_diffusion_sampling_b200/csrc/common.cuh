@@ -81,6 +81,15 @@ struct FlowParams {
     unsigned int* fix_list;       // device list, capacity n
     int fix_pass;                 // 1: this launch IS the fix-up pass (flow_simt_kernel walks fix_list)
     int log_output;               // pdf mode, T == 0, raw epilogue: store log p_base instead of p_base (D_base.log_prob)
+    // one wavefront, several materials: rows are bucketed by material ON THE DEVICE (multi.cu) into
+    // "virtual tiles" of <= 128 rows of one material; the kernels walk the tile table and switch weight sets per tile
+    int n_materials;              // 0 = single material (flow / base above)
+    const unsigned char* const* flows;   // device array [n_materials] of packed flow blobs (all of one shape)
+    const float* const* bases;           // device array [n_materials] of base-net blobs
+    const unsigned int* perm;            // [n] wavefront row of every position of the material-sorted order
+    const int4* tiles;                   // per virtual tile {material, first position, rows, first position of the material}
+    const unsigned int* n_tiles_dev;     // number of virtual tiles (device scalar)
+    const unsigned int* seg_off;         // [n_materials + 1] first position of every material in the sorted order
 };
 
 // Conditioning weight in (0,1] of a query's pdf w.r.t. rounding inside the flow -- the same three factors the

@@ -120,105 +120,153 @@ __device__ __forceinline__ void velocity(const float* __restrict__ W, int domain
     }
 }
 
+// The whole flow of one query (row i of the caller's tensors) with the staged weight set.
+template <int H, bool TANGENTS>
+__device__ __forceinline__ void simt_row(const FlowParams& P, const float* __restrict__ W, const float* __restrict__ base,
+                                         Act<H, TANGENTS> a, long long i) {
+    const int k0 = (P.domain == kDisk) ? 3 : 4;      // first PE column of layer 1
+    const float inv_t = (float)(1.0 / (double)P.T);
+    float w0, w1, wiz;
+    load_wi(P, i, w0, w1, wiz);
+
+    // layer-1 contribution of PE5(wi): constant over the T steps (the reference recomputes it
+    // every step, model.py:494)
+    if (P.T > 0) {
+        float e[kPE5];
+        positional_encoding<5>(w0, w1, e);
+#pragma unroll 4
+        for (int j = 0; j < H; ++j) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < kPE5; ++k) acc = fmaf(e[k], W[(k0 + k) * H + j], acc);
+            a.bias(j) = acc;
+        }
+    }
+
+    float x0, x1, R = 1.0f, p0 = 1.0f;
+    float wox = 0.0f, woy = 0.0f, woz = 1.0f, theta_o = 0.0f;
+    float bp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (P.mode == kModePdf) {
+        load_wo(P, i, x0, x1, wox, woy, woz);
+        theta_o = x0;
+    } else {
+        if (base) base_eval(base, w0, w1, bp);
+        if (P.x0) {
+            float2 t = reinterpret_cast<const float2*>(P.x0)[i];
+            x0 = t.x; x1 = t.y;
+        } else {
+            base_draw(P.domain, bp, P.seed, P.offset, P.first_index + i, x0, x1);
+        }
+        if (P.out_x0) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
+        if (P.mode == kModeSample) p0 = expf(base_logprob(P.domain, bp, x0, x1));
+    }
+
+    const float sgn = (P.mode == kModePdf) ? -1.0f : 1.0f;
+    for (int t = 0; t < P.T; ++t) {
+        // alpha = t/T (forward, mlp_brdf_sampling.py:27) or 1 - t/T (reverse, :78), in double then fp32
+        const float alpha = (P.mode == kModePdf) ? (float)(1.0 - (double)t / (double)P.T)
+                                                 : (float)((double)t / (double)P.T);
+        float d[2], du[2], dv[2];
+        velocity<H, TANGENTS>(W, P.domain, P.in_dim, P.n_hidden, a, x0, x1, alpha, d, du, dv);
+        if (TANGENTS) {
+            // J = I +- (1/T) dd/dx ; det = J00 J11 - J01 J10   (mlp_brdf_sampling.py:44-47 / 96-99)
+            const float j00 = 1.0f + sgn * inv_t * du[0], j01 = sgn * inv_t * dv[0];
+            const float j10 = sgn * inv_t * du[1], j11 = 1.0f + sgn * inv_t * dv[1];
+            const float det = j00 * j11 - j01 * j10;
+            R = (P.mode == kModePdf) ? R * det : R / det;
+        }
+        x0 = fmaf(sgn * inv_t, d[0], x0);
+        x1 = fmaf(sgn * inv_t, d[1], x1);
+    }
+
+    if (P.mode == kModeSample) {
+        store_sample(P, i, x0, x1, p0 * R);
+    } else if (P.mode == kModePdf) {
+        base_eval(base, w0, w1, bp);
+        const float lp = base_logprob(P.domain, bp, x0, x1);
+        if (P.log_output) P.out_pdf[i] = lp;            // model.py:393-398 / 308-317 return the LOG density
+        else store_pdf(P, i, expf(lp) * R, wiz, wox, woy, woz, theta_o);
+    } else {
+        reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
+    }
+}
+
 template <int H, bool TANGENTS>
 __global__ void __launch_bounds__(kThreads) flow_simt_kernel(const FlowParams P) {
     extern __shared__ __align__(16) float smem[];
-    // fix-up pass: the rows to recompute are fix_list[0 .. *fix_count) (written by the tensor-core kernel that ran
-    // before this launch on the same stream); most launches find an empty or tiny list and leave before staging weights
-    long long n_rows = P.n;
-    if (P.fix_pass) {
-        n_rows = (long long)min(*P.fix_count, (unsigned int)min(P.n, (long long)0xffffffffll));
-        if ((long long)blockIdx.x * kThreads >= n_rows) return;
-    }
-    const int n_w = P.flow ? f32_image_floats(P.in_dim, H, P.n_hidden) : 0;     // T == 0: base net only
+    const int n_w = (P.flow || P.n_materials > 0) ? f32_image_floats(P.in_dim, H, P.n_hidden) : 0;     // T == 0: base net only
     float* W = smem;
     float* base = W + ((n_w + 3) & ~3);
     float* act = base + ((kBaseFloats + 3) & ~3);
-    {
-        if (P.flow) {
-            const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.flow);
-            const float* src = reinterpret_cast<const float*>(P.flow + hdr->off_f32);
+    Act<H, TANGENTS> a{act + threadIdx.x};
+    auto stage = [&](const unsigned char* flow, const float* bsrc) {
+        if (flow) {
+            const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(flow);
+            const float* src = reinterpret_cast<const float*>(flow + hdr->off_f32);
             for (int i = threadIdx.x; i < n_w; i += kThreads) W[i] = src[i];
         }
-        if (P.base) for (int i = threadIdx.x; i < kBaseFloats; i += kThreads) base[i] = P.base[i];
+        if (bsrc) for (int i = threadIdx.x; i < kBaseFloats; i += kThreads) base[i] = bsrc[i];
+    };
+
+    // Three iteration spaces share ONE call site of simt_row (a second inlined copy could be contracted differently by
+    // the compiler, and a row must not depend on which launch shape computed it):
+    //   single material:        rows blockIdx.x * 128 + tid, grid-strided (fix-up pass: entries of fix_list)
+    //   multi, main pass:       virtual tiles of <= 128 rows of ONE material (multi.cu built the plan); the weight set in
+    //                           shared memory is swapped when the tile's material differs
+    //   multi, fix-up pass:     material m's flagged rows are fix_list[seg_off[m] .. + fix_count[m]), 128 per chunk
+    // In the multi modes all threads of the CTA walk the same tile / chunk sequence, so the barriers in need() are uniform.
+    const bool multi = P.n_materials > 0;
+    int staged = -1;
+    auto need = [&](int m) {
+        if (m == staged) return;
+        __syncthreads();                                   // everyone is done with the previous weight set
+        stage(P.flows[m], P.bases[m]);
+        __syncthreads();
+        staged = m;
+    };
+    long long n_rows = P.n;
+    if (!multi) {
+        // fix-up pass: the rows to recompute are fix_list[0 .. *fix_count) (written by the tensor-core kernel that ran
+        // before this launch on the same stream); most launches find an empty or tiny list and leave before staging weights
+        if (P.fix_pass) {
+            n_rows = (long long)min(*P.fix_count, (unsigned int)min(P.n, (long long)0xffffffffll));
+            if ((long long)blockIdx.x * kThreads >= n_rows) return;
+        }
+        stage(P.flow, P.base);
+        __syncthreads();
     }
-    __syncthreads();
-    Act<H, TANGENTS> a{act + threadIdx.x};
-    const int k0 = (P.domain == kDisk) ? 3 : 4;      // first PE column of layer 1
-    const float inv_t = (float)(1.0 / (double)P.T);
-
-    for (long long jj = (long long)blockIdx.x * kThreads + threadIdx.x; jj < n_rows;
-         jj += (long long)gridDim.x * kThreads) {
-        const long long i = P.fix_pass ? (long long)P.fix_list[jj] : jj;
-        float w0, w1, wiz;
-        load_wi(P, i, w0, w1, wiz);
-
-        // layer-1 contribution of PE5(wi): constant over the T steps (the reference recomputes it
-        // every step, model.py:494)
-        if (P.T > 0) {
-            float e[kPE5];
-            positional_encoding<5>(w0, w1, e);
-#pragma unroll 4
-            for (int j = 0; j < H; ++j) {
-                float acc = 0.0f;
-#pragma unroll
-                for (int k = 0; k < kPE5; ++k) acc = fmaf(e[k], W[(k0 + k) * H + j], acc);
-                a.bias(j) = acc;
-            }
-        }
-
-        float x0, x1, R = 1.0f, p0 = 1.0f;
-        float wox = 0.0f, woy = 0.0f, woz = 1.0f, theta_o = 0.0f;
-        float bp[4] = {0.f, 0.f, 0.f, 0.f};
-        if (P.mode == kModePdf) {
-            load_wo(P, i, x0, x1, wox, woy, woz);
-            theta_o = x0;
+    const float* bptr = (multi || P.base) ? base : nullptr;
+    const unsigned int n_tiles = (multi && !P.fix_pass) ? *P.n_tiles_dev : 0u;
+    long long jj = (long long)blockIdx.x * kThreads + threadIdx.x;       // single
+    unsigned int k = blockIdx.x;                                         // multi main: tile; multi fix: chunk of material m
+    int m = 0;
+    for (;;) {
+        long long i = -1;
+        if (!multi) {
+            if (jj >= n_rows) break;
+            i = P.fix_pass ? (long long)P.fix_list[jj] : jj;
+            jj += (long long)gridDim.x * kThreads;
+        } else if (!P.fix_pass) {
+            if (k >= n_tiles) break;
+            const int4 ti = P.tiles[k];
+            need(ti.x);
+            if ((int)threadIdx.x < ti.z) i = (long long)P.perm[ti.y + threadIdx.x];
+            k += gridDim.x;
         } else {
-            if (P.base) base_eval(base, w0, w1, bp);
-            if (P.x0) {
-                float2 t = reinterpret_cast<const float2*>(P.x0)[i];
-                x0 = t.x; x1 = t.y;
-            } else {
-                base_draw(P.domain, bp, P.seed, P.offset, P.first_index + i, x0, x1);
-            }
-            if (P.out_x0) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
-            if (P.mode == kModeSample) p0 = expf(base_logprob(P.domain, bp, x0, x1));
+            while (m < P.n_materials && (unsigned long long)k * kThreads >= P.fix_count[m]) { ++m; k = blockIdx.x; }
+            if (m >= P.n_materials) break;
+            need(m);
+            const unsigned int e = k * kThreads + threadIdx.x;
+            if (e < P.fix_count[m]) i = (long long)P.fix_list[P.seg_off[m] + e];
+            k += gridDim.x;
         }
-
-        const float sgn = (P.mode == kModePdf) ? -1.0f : 1.0f;
-        for (int t = 0; t < P.T; ++t) {
-            // alpha = t/T (forward, mlp_brdf_sampling.py:27) or 1 - t/T (reverse, :78), in double then fp32
-            const float alpha = (P.mode == kModePdf) ? (float)(1.0 - (double)t / (double)P.T)
-                                                     : (float)((double)t / (double)P.T);
-            float d[2], du[2], dv[2];
-            velocity<H, TANGENTS>(W, P.domain, P.in_dim, P.n_hidden, a, x0, x1, alpha, d, du, dv);
-            if (TANGENTS) {
-                // J = I +- (1/T) dd/dx ; det = J00 J11 - J01 J10   (mlp_brdf_sampling.py:44-47 / 96-99)
-                const float j00 = 1.0f + sgn * inv_t * du[0], j01 = sgn * inv_t * dv[0];
-                const float j10 = sgn * inv_t * du[1], j11 = 1.0f + sgn * inv_t * dv[1];
-                const float det = j00 * j11 - j01 * j10;
-                R = (P.mode == kModePdf) ? R * det : R / det;
-            }
-            x0 = fmaf(sgn * inv_t, d[0], x0);
-            x1 = fmaf(sgn * inv_t, d[1], x1);
-        }
-
-        if (P.mode == kModeSample) {
-            store_sample(P, i, x0, x1, p0 * R);
-        } else if (P.mode == kModePdf) {
-            base_eval(base, w0, w1, bp);
-            const float lp = base_logprob(P.domain, bp, x0, x1);
-            if (P.log_output) P.out_pdf[i] = lp;            // model.py:393-398 / 308-317 return the LOG density
-            else store_pdf(P, i, expf(lp) * R, wiz, wox, woy, woz, theta_o);
-        } else {
-            reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
-        }
+        if (i >= 0) simt_row<H, TANGENTS>(P, W, bptr, a, i);
     }
 }
 
 template <int H, bool TANGENTS>
 static int launch_simt_t(const FlowParams& P, cudaStream_t stream) {
-    const int n_w = P.flow ? f32_image_floats(P.in_dim, H, P.n_hidden) : 0;
+    const int n_w = (P.flow || P.n_materials > 0) ? f32_image_floats(P.in_dim, H, P.n_hidden) : 0;
     const int rows = (TANGENTS ? 4 : 2) * H;
     const size_t smem = sizeof(float) * (((n_w + 3) & ~3) + ((kBaseFloats + 3) & ~3) + (size_t)rows * kThreads);
     auto kern = flow_simt_kernel<H, TANGENTS>;
@@ -227,7 +275,7 @@ static int launch_simt_t(const FlowParams& P, cudaStream_t stream) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) return -3;
-    long long tiles = (P.n + kThreads - 1) / kThreads;
+    long long tiles = (P.n_materials > 0) ? P.n / kThreads + P.n_materials : (P.n + kThreads - 1) / kThreads;
     long long grid = (long long)sms * occ;
     if (grid > tiles) grid = tiles;
     if (grid < 1) return 0;

@@ -112,7 +112,8 @@ constexpr int kFP0 = 13;                           // base density at the start 
 constexpr int kFBp = 14;                           // 4 base-net outputs (pdf mode evaluates the base density at the end)
 constexpr int kFWiz = 18;                          // wi_z, wo (pdf-mode masks)
 constexpr int kFWo = 19;
-constexpr int kFields = 22;
+constexpr int kFIdx = 22;                          // multi-material launches: wavefront row of this tile row (int bits), -1 = padding row
+constexpr int kFields = 23;
 constexpr int kTile = 128;
 #if BSDFDIFF_TC_GROUPS == 5
 // Five tiles in flight: 96 columns per tile.  The v-tangent operand goes through shared memory (SS-form MMA), A_h sits
@@ -482,20 +483,25 @@ __device__ __forceinline__ void base_draw_fast(const float p[4], unsigned long l
 
 // Append row i to the fix-up list (warp-aggregated: one atomic per warp that has any flagged row).  Called by all 32
 // lanes of a converged worker warp.
-__device__ __forceinline__ void flag_for_fixup(const FlowParams& P, bool flag, long long i) {
+// Multi-material launches keep one list per material (a warp's rows share a tile, hence a material): material m's
+// list lives at fix_list[seg_off[m] ...] -- it can never outgrow the material's own row count -- with its length in
+// fix_count[m], so the fix-up pass can stage one weight set per chunk of rows.
+__device__ __forceinline__ void flag_for_fixup(const FlowParams& P, bool flag, long long i, int mat = -1) {
     const uint32_t mask = __ballot_sync(0xffffffffu, flag);
     if (mask == 0u) return;
     const int lane = threadIdx.x & 31;
+    unsigned int* count = (mat >= 0) ? P.fix_count + mat : P.fix_count;
+    unsigned int* list = (mat >= 0) ? P.fix_list + P.seg_off[mat] : P.fix_list;
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(P.fix_count, (unsigned int)__popc(mask));
+    if (lane == 0) base = atomicAdd(count, (unsigned int)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (flag) P.fix_list[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned int)i;
+    if (flag) list[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned int)i;
 }
 
 struct TcSmem {
     unsigned long long d_ready[kGroups];
     unsigned int arrive[kGroups];             // duo, issue mode 2: warps that have stored their rows of the pipe's current round
-    unsigned long long w_bar;
+    unsigned long long w_bar[kGroups];        // weights landed (single material: [0] only; multi: one image per group)
     unsigned long long full[kSlots];          // producer -> worker group: the slot's records are written
     unsigned long long empty[kSlots];         // worker group -> producer: the slot has been read
     uint32_t tmem_base;
@@ -509,8 +515,11 @@ struct TcSmem {
     __align__(128) unsigned char av[kSmemAv ? kGroups : 1][kSmemAv ? kAvBytes : 128];   // v-tangent operands (5-tile map)
     __align__(128) unsigned char w16[128];    // hi+lo operand images of every layer: dynamic tail, hdr->f16_bytes long
 };
-static inline size_t tc_smem_bytes(int H, int n_hidden) {
-    return offsetof(TcSmem, w16) + sizeof(__half) * (size_t)f16_image_halves(H, n_hidden);
+static inline size_t tc_image_bytes(int H, int n_hidden) {
+    return (sizeof(__half) * (size_t)f16_image_halves(H, n_hidden) + 127) / 128 * 128;
+}
+static inline size_t tc_smem_bytes(int H, int n_hidden, bool multi) {
+    return offsetof(TcSmem, w16) + (multi ? kGroups : 1) * tc_image_bytes(H, n_hidden);
 }
 
 // base net p = Wo silu(W1 PE3(e) + b1) + bo from the shared-memory copy (rendering/utils/model.py:382-386)
@@ -814,17 +823,19 @@ __device__ __forceinline__ void raw_load(const FlowParams& P, long long i, RawIn
 //                 serial FMA chains); on its own warps it fills the issue slots the workers leave idle while they
 //                 wait for MMAs instead of adding ~1/3 to every tile's critical path (profiles/r1d vs r1h).
 // ------------------------------------------------------------------------------------------------
-template <int DOMAIN, int MODE, int ACT, int H>
+template <int DOMAIN, int MODE, int ACT, int H, bool MULTI>
 __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams P) {
     constexpr bool TANGENTS = (MODE != kModeForward);
+    static_assert(!MULTI || (!kDuo && !kSmemAv), "multi-material launches use the one-tile-per-thread worker structure");
     static_assert(H == 32 || (H == 64 && !TANGENTS), "64-wide nets: forward-only (reflow teacher) rounds");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     // warp index through a shuffle so the compiler can prove it warp-uniform: TMEM addresses and MMA
     // descriptors then live in uniform registers (no per-MMA R2UR/ELECT waterfall)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-    const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.flow);
+    const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(MULTI ? P.flows[0] : P.flow);   // multi: all blobs share one shape
     const int NH = P.n_hidden;
+    const uint32_t img_bytes = (hdr->f16_bytes + 127u) & ~127u;                  // multi: one weight image per group
 
     // ---- one-time setup ---------------------------------------------------------------------------
     if (threadIdx.x == 0) {
@@ -833,13 +844,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             mbar_init(smem_u32(&S.full[sl]), kProducerWarps);      // one arrival per producer warp
             mbar_init(smem_u32(&S.empty[sl]), 4);                  // one arrival per warp of the consuming group
         }
-        mbar_init(smem_u32(&S.w_bar), 1);
+        for (int g = 0; g < kGroups; ++g) mbar_init(smem_u32(&S.w_bar[g]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t f16_bytes = hdr->f16_bytes;
-        mbar_expect_tx(smem_u32(&S.w_bar), f16_bytes);
-        tma_bulk_g2s(smem_u32(S.w16), P.flow + hdr->off_f16, f16_bytes, smem_u32(&S.w_bar));
+        if (!MULTI) {
+            const uint32_t f16_bytes = hdr->f16_bytes;
+            mbar_expect_tx(smem_u32(&S.w_bar[0]), f16_bytes);
+            tma_bulk_g2s(smem_u32(S.w16), P.flow + hdr->off_f16, f16_bytes, smem_u32(&S.w_bar[0]));
+        }
     }
-    if (P.base) {
+    if (!MULTI && P.base) {
         for (int i = threadIdx.x; i < kPE3 * 16; i += kTcThreads) {          // w1t[k][j] = W1[j][k]
             const int k = i >> 4, j = i & 15;
             S.bw1t[i] = P.base[j * kPE3 + k];
@@ -861,7 +874,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
 
-    const long long n_tiles = (P.n + kTile - 1) / kTile;
+    const long long n_tiles = MULTI ? (long long)*P.n_tiles_dev : (P.n + kTile - 1) / kTile;
     // tile list of this CTA: blockIdx.x, +gridDim.x, ...; entry k goes to group k % kGroups through slot k % kSlots
     const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
@@ -871,19 +884,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         RawIn cur, nxt;
         cur.wa = cur.wb = cur.wc = cur.oa = cur.ob = cur.oc = cur.r0 = cur.r1 = 0.0f;
         nxt = cur;
+        int mat_n = 0;                                      // material of the tile index_of looked at last
         auto index_of = [&](long long k, bool& valid) {
+            if (MULTI) {
+                const int4 ti = P.tiles[blockIdx.x + k * gridDim.x];
+                mat_n = ti.x;
+                valid = row < ti.z;
+                return (long long)P.perm[ti.y + (valid ? row : 0)];   // padding rows recompute the tile's first row, never store
+            }
             const long long i_raw = (blockIdx.x + k * gridDim.x) * kTile + row;
             valid = i_raw < P.n;
             return valid ? i_raw : (P.n - 1);               // tail rows recompute the last query, never store
         };
         bool valid = false, valid_n = false;
         long long i = 0, i_n = 0;
+        int mat = -1, mat_staged = -1;
         int sl = 0;                                         // ring position of tile k: k % kSlots, lap k / kSlots
         uint32_t use = 0;
-        if (my_tiles > 0) { i = index_of(0, valid); raw_load<MODE>(P, i, cur); }
+        if (my_tiles > 0) { i = index_of(0, valid); mat = mat_n; raw_load<MODE>(P, i, cur); }
 #pragma unroll 1
         for (long long k = 0; k < my_tiles; ++k) {
-            if (k + 1 < my_tiles) { i_n = index_of(k + 1, valid_n); raw_load<MODE>(P, i_n, nxt); }
+            const int mat_cur = mat;
+            if (k + 1 < my_tiles) { i_n = index_of(k + 1, valid_n); mat = mat_n; raw_load<MODE>(P, i_n, nxt); }
+            if (MULTI && mat_cur != mat_staged) {
+                // this tile's material differs from the staged base net: the 128 producer threads re-stage it
+                // (only they read it; named barrier 15 keeps the four producer warps in step)
+                asm volatile("bar.sync 15, 128;" ::: "memory");
+                const float* bsrc = P.bases[mat_cur];
+                const int t = row;
+                for (int q2 = t; q2 < kPE3 * 16; q2 += 128) S.bw1t[q2] = bsrc[(q2 & 15) * kPE3 + (q2 >> 4)];
+                if (t < 16) S.bb1[t] = bsrc[224 + t];
+                if (t < 64) S.bwot[t] = bsrc[240 + (t & 3) * 16 + (t >> 2)];
+                if (t < 4) S.bbo[t] = bsrc[304 + t];
+                asm volatile("bar.sync 15, 128;" ::: "memory");
+                mat_staged = mat_cur;
+            }
             // conditioning in domain coordinates (brdf_measured_disk.py:66-67, brdf_measured_spherical.py:76-77)
             float w0, w1, wiz = cur.wc;
             if (P.epilogue == kEpiRaw || P.epilogue == kEpiDisk) { w0 = cur.wa; w1 = cur.wb; }
@@ -894,7 +929,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 #pragma unroll
             for (int j = 0; j < 11; ++j) c[j] = pack_h2(e[2 * j], e[2 * j + 1]);
             float bp[4] = {0.f, 0.f, 0.f, 0.f};
-            if (P.base) base_eval_smem(S, e, bp);               // PE3 is a prefix of PE5
+            if (MULTI || P.base) base_eval_smem(S, e, bp);      // PE3 is a prefix of PE5
             float x0, x1, p0 = 1.0f;
             if (MODE == kModePdf) {
                 if (P.epilogue == kEpiRaw || P.epilogue == kEpiDisk) { x0 = cur.oa; x1 = cur.ob; }   // brdf_measured_disk.py:118-120
@@ -918,6 +953,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 f[kFWiz][row] = wiz;
                 f[kFWo][row] = cur.oa; f[kFWo + 1][row] = cur.ob; f[kFWo + 2][row] = cur.oc;
             }
+            if (MULTI) f[kFIdx][row] = __int_as_float(valid ? (int)i : -1);
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&S.full[sl]));      // release: the stores above are visible to the waiters
             cur = nxt; i = i_n; valid = valid_n;
@@ -933,7 +969,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         asm volatile("" : "+l"(b_out));
         const float inv_t = (float)(1.0 / (double)P.T);
         const float step = (MODE == kModePdf) ? -inv_t : inv_t;
-        mbar_wait(smem_u32(&S.w_bar), 0);                                       // weights have landed in smem (any warp may issue)
+        mbar_wait(smem_u32(&S.w_bar[0]), 0);                                    // weights have landed in smem (any warp may issue)
 
         // one turn of tile slot SLOT (0 | 1) of this thread: pipe = g + 2 SLOT (both groups get a tile before either gets two)
         auto turn = [&](auto slot_tag, Pipe& p) {
@@ -1048,7 +1084,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         const uint32_t tg_mma = tmem_base + g * kColsPerGroup;                   // lane field 0: MMA operand addresses
         const uint32_t tg = tg_mma + ((uint32_t)(q * 32) << 16);                 // this warp's 32-lane window
         const uint32_t bar_d = smem_u32(&S.d_ready[g]);
-        const uint32_t w_base = smem_u32(S.w16);
+        const uint32_t w_base = smem_u32(S.w16) + (MULTI ? (uint32_t)g * img_bytes : 0u);   // multi: this group's own weight image
         const uint64_t b_hid0 = make_b_desc(w_base, H * 16, 128);                // first / hidden layers: N = H rows
         uint64_t b_out = make_b_desc(w_base + 2u * H * 32u * 2u + (uint32_t)(NH - 1) * (2u * H * H * 2u), 256, 128);   // N = 16
         uint64_t av_desc = kSmemAv ? make_b_desc(smem_u32(S.av[kSmemAv ? g : 0]), 2048, 128) : 0ull;   // A image: LBO 2048, SBO 128
@@ -1059,15 +1095,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         uint32_t use = 0;
         const float inv_t = (float)(1.0 / (double)P.T);
         const float step = (MODE == kModePdf) ? -inv_t : inv_t;
-        if (q == 0) mbar_wait(smem_u32(&S.w_bar), 0);                           // weights have landed in smem
+        if (!MULTI && q == 0) mbar_wait(smem_u32(&S.w_bar[0]), 0);              // weights have landed in smem
+        int mat = 0, mat_staged = -1;                                           // multi: material of this tile / of the group's image
+        uint32_t wpar = 0;
         int trace_r = 0;
         (void)trace_r;
 
 #pragma unroll 1
         for (long long k = g; k < my_tiles; k += kGroups) {
-            const long long i_raw = (blockIdx.x + k * gridDim.x) * kTile + row;
-            const bool valid = i_raw < P.n;
-            const long long i = valid ? i_raw : (P.n - 1);
+            long long i_raw = (blockIdx.x + k * gridDim.x) * kTile + row;
+            bool valid = i_raw < P.n;
+            if (MULTI) {
+                // the tile's material: its weight image replaces the group's previous one.  Every MMA that read the old
+                // image has completed (all four warps waited for the previous tile's last round), and only this warp
+                // issues the group's MMAs, so it alone has to see the new image land.
+                mat = P.tiles[blockIdx.x + k * gridDim.x].x;
+                if (q == 0 && mat != mat_staged) {
+                    if (elect_one()) {
+                        const unsigned char* blob = P.flows[mat];
+                        const PackedHeader* h2 = reinterpret_cast<const PackedHeader*>(blob);
+                        const uint32_t bytes = h2->f16_bytes;
+                        mbar_expect_tx(smem_u32(&S.w_bar[g]), bytes);
+                        tma_bulk_g2s(w_base, blob + h2->off_f16, bytes, smem_u32(&S.w_bar[g]));
+                    }
+                    __syncwarp();
+                    mbar_wait(smem_u32(&S.w_bar[g]), wpar); wpar ^= 1u;
+                }
+                mat_staged = mat;
+            }
 
             // ---- take this row's record from the producer ----
             float x0, x1, R = 1.0f, p0 = 1.0f;
@@ -1077,6 +1132,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
             const float (*f)[kTile] = S.slot[sl];
             x0 = f[kFX][row]; x1 = f[kFX + 1][row];
             if (MODE == kModeSample) p0 = f[kFP0][row];
+            if (MULTI) {                                     // wavefront row of this tile row (-1: padding row)
+                const int idx = __float_as_int(f[kFIdx][row]);
+                valid = idx >= 0;
+                i_raw = idx;
+            }
+            const long long i = valid ? i_raw : (MULTI ? 0 : P.n - 1);
             const float theta_o = x0;
 
 #pragma unroll 1
@@ -1124,7 +1185,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
             if (MODE == kModeSample) {
                 if (valid) store_sample<true>(P, i, x0, x1, p0 * R);
-                if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && cond.weight() < P.fix_thr, i);
+                if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && cond.weight() < P.fix_thr, i, MULTI ? mat : -1);
             } else if (MODE == kModePdf) {
                 float bp[4];
 #pragma unroll
@@ -1137,7 +1198,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 if (P.fix_thr > 0.0f) {
                     const float kappa = (DOMAIN == kDisk) ? 0.0f : softplus_fast(bp[3]) + 1e-3f;
                     const float gn = base_grad_norm(DOMAIN, bp, kappa, x0, x1);
-                    flag_for_fixup(P, valid && cond.weight() * fminf(1.0f, __fdividef(25.0f, gn)) < P.fix_thr, i);
+                    flag_for_fixup(P, valid && cond.weight() * fminf(1.0f, __fdividef(25.0f, gn)) < P.fix_thr, i,
+                                   MULTI ? mat : -1);
                 }
             } else {
                 if (valid) reinterpret_cast<float2*>(P.out_dir)[i] = make_float2(x0, x1);
@@ -1157,27 +1219,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     }
 }
 
-template <int DOMAIN, int MODE, int ACT, int H>
+template <int DOMAIN, int MODE, int ACT, int H, bool MULTI = false>
 static int launch_tc_t(const FlowParams& P, cudaStream_t stream) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles = (P.n + kTile - 1) / kTile;
+    // multi-material launches: the number of virtual tiles is only known on the device (<= n / 128 + n_materials)
+    const long long tiles = MULTI ? P.n / kTile + P.n_materials : (P.n + kTile - 1) / kTile;
     long long grid = sms;
     if (grid > tiles) grid = tiles;
     if (grid < 1) return 0;
-    const size_t smem = tc_smem_bytes(H, P.n_hidden);
+    const size_t smem = tc_smem_bytes(H, P.n_hidden, MULTI);
     if (smem > 227u * 1024u) return -2;
     // the opt-in is per DEVICE (a process may drive several GPUs): set it on every launch, like launch_simt_t does --
     // cheap and CUDA-graph-capture safe
-    if (cudaFuncSetAttribute(flow_tc_kernel<DOMAIN, MODE, ACT, H>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(flow_tc_kernel<DOMAIN, MODE, ACT, H, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)smem) != cudaSuccess) return -3;
-    flow_tc_kernel<DOMAIN, MODE, ACT, H><<<(unsigned)grid, kTcThreads, smem, stream>>>(P);
+    flow_tc_kernel<DOMAIN, MODE, ACT, H, MULTI><<<(unsigned)grid, kTcThreads, smem, stream>>>(P);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 template <int DOMAIN, int ACT>
 static int launch_tc_m(const FlowParams& P, cudaStream_t stream) {
+    if (P.n_materials > 0) {                  // one wavefront, several materials: sampler shapes only
+        if (P.hidden != 32 || kDuo || kSmemAv) return -2;
+#if !BSDFDIFF_TC_DUO && BSDFDIFF_TC_GROUPS != 5
+        if (P.mode == kModeSample) return launch_tc_t<DOMAIN, kModeSample, ACT, 32, true>(P, stream);
+        if (P.mode == kModePdf) return launch_tc_t<DOMAIN, kModePdf, ACT, 32, true>(P, stream);
+#endif
+        return -2;
+    }
     if (P.hidden == 64) {                     // reflow teacher nets (NN_cond_pos_spherical_complicate): forward only
         if (P.mode != kModeForward) return -2;
         return launch_tc_t<DOMAIN, kModeForward, ACT, 64>(P, stream);

@@ -235,6 +235,160 @@ def _(x, flow_blob, precision, hidden, n_hidden):
     return x.new_empty((x.shape[0], 2))
 
 
+# ---- one wavefront, several materials (include/bsdfdiff.h: bsdfdiff_multi_plan / _sample_multi / _pdf_multi) ----------
+@torch.library.custom_op("bsdfdiff::multi_plan", mutates_args=(), device_types="cuda")
+def _multi_plan_op(material_id: torch.Tensor, n_materials: int) -> torch.Tensor:
+    n = material_id.shape[0]
+    scratch = torch.empty((_lib.lib.bsdfdiff_multi_scratch_bytes(n, n_materials) + 3) // 4, dtype=torch.int32,
+                          device=material_id.device)
+    with torch.cuda.device(material_id.device):
+        rc = _lib.lib.bsdfdiff_multi_plan(n, material_id.data_ptr(), n_materials, scratch.data_ptr(),
+                                          _stream(material_id))
+    _lib.check(rc, "bsdfdiff_multi_plan")
+    return scratch
+
+
+@_multi_plan_op.register_fake
+def _(material_id, n_materials):
+    return material_id.new_empty((1280 + 4 * (material_id.shape[0] // 128 + n_materials + 1) + 4 * material_id.shape[0],),
+                                 dtype=torch.int32)
+
+
+@torch.library.custom_op("bsdfdiff::sample_multi", mutates_args=("plan",), device_types="cuda")
+def _sample_multi_op(wi: torch.Tensor, plan: torch.Tensor, flows: torch.Tensor, bases: torch.Tensor,
+                     x0: Optional[torch.Tensor], precision: int, domain: int, epilogue: int, T: int, hidden: int,
+                     n_hidden: int, seed: int, offset: int, first_index: int,
+                     fix_thr: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    n = wi.shape[0]
+    out_dir = torch.empty((n, 2 if epilogue == EPI_RAW else 3), dtype=torch.float32, device=wi.device)
+    out_pdf = torch.empty((n,), dtype=torch.float32, device=wi.device)
+    with torch.cuda.device(wi.device):
+        rc = _lib.lib.bsdfdiff_sample_multi(precision, domain, epilogue, T, n, wi.data_ptr(), plan.data_ptr(),
+                                            flows.shape[0], flows.data_ptr(), bases.data_ptr(), hidden, n_hidden,
+                                            x0.data_ptr() if x0 is not None else None, seed, offset, first_index,
+                                            out_dir.data_ptr(), out_pdf.data_ptr(), None, fix_thr, _stream(wi))
+    _lib.check(rc, "bsdfdiff_sample_multi")
+    return out_dir, out_pdf
+
+
+@_sample_multi_op.register_fake
+def _(wi, plan, flows, bases, x0, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, fix_thr):
+    n = wi.shape[0]
+    return wi.new_empty((n, 2 if epilogue == EPI_RAW else 3)), wi.new_empty((n,))
+
+
+@torch.library.custom_op("bsdfdiff::pdf_multi", mutates_args=("plan",), device_types="cuda")
+def _pdf_multi_op(wo: torch.Tensor, wi: torch.Tensor, plan: torch.Tensor, flows: torch.Tensor, bases: torch.Tensor,
+                  precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
+                  fix_thr: float) -> torch.Tensor:
+    n = wi.shape[0]
+    out = torch.empty((n,), dtype=torch.float32, device=wi.device)
+    with torch.cuda.device(wi.device):
+        rc = _lib.lib.bsdfdiff_pdf_multi(precision, domain, epilogue, T, n, wo.data_ptr(), wi.data_ptr(),
+                                         plan.data_ptr(), flows.shape[0], flows.data_ptr(), bases.data_ptr(), hidden,
+                                         n_hidden, out.data_ptr(), fix_thr, _stream(wi))
+    _lib.check(rc, "bsdfdiff_pdf_multi")
+    return out
+
+
+@_pdf_multi_op.register_fake
+def _(wo, wi, plan, flows, bases, precision, domain, epilogue, T, hidden, n_hidden, fix_thr):
+    return wi.new_empty((wi.shape[0],))
+
+
+class MultiPlan:
+    """Device-side bucketing of one wavefront's rows by material id (no host read).  Reusable by any number of
+    ``sample_multi`` / ``pdf_multi`` calls on the same ``material_id`` column (they must be stream-ordered: the plan
+    buffer also holds the per-call fix-up lists)."""
+
+    def __init__(self, material_id: torch.Tensor, n_materials: int):
+        _require_cuda(material_id, "multi_plan")
+        if material_id.dim() != 1 or material_id.dtype not in (torch.int32, torch.int64):
+            raise TypeError("material_id must be a 1-D int32 / int64 tensor")
+        if not 1 <= int(n_materials) <= 255:
+            raise ValueError("1 <= n_materials <= 255")
+        if material_id.shape[0] >= 2 ** 31:
+            raise ValueError("a multi-material wavefront holds fewer than 2^31 rows")
+        self.n, self.n_materials = material_id.shape[0], int(n_materials)
+        self.scratch = _multi_plan_op(material_id.to(torch.int32).contiguous(), self.n_materials)
+
+    def counts(self) -> torch.Tensor:
+        """Rows per material [n_materials] plus the inactive rows (last entry); device tensor (diagnostics)."""
+        return self.scratch[: self.n_materials + 1]
+
+    def fixup_counts(self) -> torch.Tensor:
+        """Rows the last tc16 call on this plan recomputed in fp32, per material (device tensor; diagnostics)."""
+        return self.scratch[1024:1024 + self.n_materials]
+
+
+class MaterialTable:
+    """Device pointer tables of a scene's material set: packed flow blobs and base-net blobs of one shape."""
+
+    def __init__(self, flows, bases):
+        flows, bases = list(flows), list(bases)
+        if not flows or len(flows) != len(bases):
+            raise ValueError("need one base net per flow net")
+        f0 = flows[0]
+        for f in flows:
+            if (f.domain, f.hidden, f.n_hidden, f.in_dim) != (f0.domain, f0.hidden, f0.n_hidden, f0.in_dim):
+                raise ValueError("all materials of one table must share the flow-net shape")
+        dev = f0.blob.device
+        for t in [f.blob for f in flows] + bases:
+            if t.device != dev:
+                raise ValueError("all material blobs must live on one device")
+        self.flows, self.bases = flows, bases         # keep the blobs alive
+        self.domain, self.hidden, self.n_hidden, self.in_dim = f0.domain, f0.hidden, f0.n_hidden, f0.in_dim
+        self.flow_ptrs = torch.tensor([f.blob.data_ptr() for f in flows], dtype=torch.int64, device=dev)
+        self.base_ptrs = torch.tensor([b.data_ptr() for b in bases], dtype=torch.int64, device=dev)
+
+    def __len__(self):
+        return len(self.flows)
+
+
+def _check_multi(table: MaterialTable, plan: MultiPlan, wi: torch.Tensor, T: int, what: str) -> None:
+    if T < 1:
+        raise ValueError("T must be >= 1")
+    if table.in_dim not in (25, 26):
+        raise ValueError(f"bsdfdiff.{what}: the sampler nets take 25 (disk) or 26 (spherical) inputs")
+    if plan.n != wi.shape[0] or plan.n_materials != len(table):
+        raise ValueError(f"bsdfdiff.{what}: the plan was built for {plan.n} rows / {plan.n_materials} materials, "
+                         f"got {wi.shape[0]} rows / {len(table)} materials")
+    if plan.scratch.device != wi.device or table.flow_ptrs.device != wi.device:
+        raise ValueError(f"bsdfdiff.{what}: wavefront, plan and material table must live on one device")
+
+
+def sample_multi(wi: torch.Tensor, plan: MultiPlan, table: MaterialTable, T: int, *, epilogue: int = EPI_RAW,
+                 x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0, first_index: int = 0,
+                 precision=None, fixup=None):
+    """One launch for a wavefront with a material id per row -> (dir [n,2|3], pdf [n]) in wavefront order."""
+    _require_cuda(wi, "sample_multi")
+    wi = _f32c(wi)
+    _check_rows(wi, wi.shape[0], 2 if epilogue == EPI_RAW else 3, "wi")
+    _check_multi(table, plan, wi, T, "sample_multi")
+    if x0 is not None:
+        x0 = _f32c(x0, wi.device)
+        _check_rows(x0, wi.shape[0], 2, "x0")
+        seed, offset = 0, 0
+    elif seed is None:
+        seed, offset = next_philox(wi.device)
+    return _sample_multi_op(wi, plan.scratch, table.flow_ptrs, table.base_ptrs, x0, _resolve_precision(precision),
+                            table.domain, epilogue, int(T), table.hidden, table.n_hidden, int(seed), int(offset),
+                            int(first_index), _fix_thr(fixup))
+
+
+def pdf_multi(wo: torch.Tensor, wi: torch.Tensor, plan: MultiPlan, table: MaterialTable, T: int, *,
+              epilogue: int = EPI_RAW, precision=None, fixup=None) -> torch.Tensor:
+    _require_cuda(wi, "pdf_multi")
+    wi = _f32c(wi)
+    wo = _f32c(wo, wi.device)
+    cols = 2 if epilogue == EPI_RAW else 3
+    _check_rows(wi, wi.shape[0], cols, "wi")
+    _check_rows(wo, wi.shape[0], cols, "wo")
+    _check_multi(table, plan, wi, T, "pdf_multi")
+    return _pdf_multi_op(wo, wi, plan.scratch, table.flow_ptrs, table.base_ptrs, _resolve_precision(precision),
+                         table.domain, epilogue, int(T), table.hidden, table.n_hidden, _fix_thr(fixup))
+
+
 # ------------------------------------------------------------------------------------------------
 # friendly wrappers
 # ------------------------------------------------------------------------------------------------

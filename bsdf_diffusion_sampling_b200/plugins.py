@@ -193,69 +193,60 @@ class NeuralBSDFSampler:
 
 
 class MultiMaterialSampler:
-    """One wavefront, several ``mybsdf`` instances.
+    """One wavefront, several ``mybsdf`` instances, ONE launch.
 
     The reference's array scenes hold twelve ``mybsdf`` BSDFs (``matpreview/disney_bsdf_array0_envmap.xml:35-335``);
-    Mitsuba calls each instance with the lanes that hit it.  A renderer that keeps ONE wavefront with a material id
-    per lane calls this instead: rows are bucketed by material with a stable sort (one ``torch.sort`` + one
-    ``bincount``), each bucket is one launch of that material's fused kernel on the current stream, and the results
-    are scattered back into wavefront order -- no host synchronisation besides reading the bucket sizes.
-    Philox counters are ``first_index`` + position inside the bucket order, so a call is deterministic for a given
-    (seed, offset, material_id) but, unlike the single-material path, depends on the bucketing."""
+    Mitsuba calls each instance with the lanes that hit it.  A renderer that keeps one wavefront with a material id per
+    lane calls this instead: ``plan(material_id)`` buckets the rows by material on the device (no host read), and
+    ``sample`` / ``pdf`` run one persistent kernel that walks the plan's 128-row single-material tiles, switching the
+    weight set in shared memory per tile.  Every row is read and written at its wavefront position with the Philox
+    counter ``first_index + row``, so row i equals ``samplers[material_id[i]].sample(wi)[i]`` bit for bit -- nothing
+    depends on the bucketing.  Rows with an id outside ``[0, len(samplers))`` are inactive lanes: outputs zeroed."""
 
     def __init__(self, samplers):
         self.samplers = list(samplers)
         if not self.samplers:
             raise ValueError("need at least one material")
-        if len({s.kind for s in self.samplers}) != 1:
-            raise ValueError("all materials of one MultiMaterialSampler must share a plugin kind")
+        s0 = self.samplers[0]
+        for s in self.samplers:
+            if (s.kind, s.T, s.precision, s.fixup) != (s0.kind, s0.T, s0.precision, s0.fixup):
+                raise ValueError("all materials of one MultiMaterialSampler must share plugin kind, T, precision and fix-up threshold")
+        self.kind, self.T, self.epilogue, self.precision, self.fixup = s0.kind, s0.T, s0.epilogue, s0.precision, s0.fixup
+        self.table = ops.MaterialTable([s.flow for s in self.samplers], [s.base for s in self.samplers])
 
-    def _buckets(self, material_id: torch.Tensor):
-        if material_id.dtype not in (torch.int32, torch.int64):
-            raise TypeError("material_id must be an integer tensor")
-        mid = material_id.to(torch.int64)
-        if mid.numel() and (int(mid.min()) < 0 or int(mid.max()) >= len(self.samplers)):
-            raise IndexError("material id out of range")
-        order = torch.sort(mid, stable=True).indices
-        counts = torch.bincount(mid, minlength=len(self.samplers)).tolist()        # the one host read
-        return order, counts
+    def plan(self, material_id: torch.Tensor) -> "ops.MultiPlan":
+        """Bucket the wavefront once; reuse the plan for ``sample`` and the ``pdf`` calls of the same bounce."""
+        return ops.MultiPlan(material_id, len(self.samplers))
 
-    def sample(self, wi: torch.Tensor, material_id: torch.Tensor, *, x0=None, seed=None, offset=0, first_index=0):
-        """wi [N,3], material_id [N] -> (wo [N,3], pdf [N]) in wavefront order."""
-        order, counts = self._buckets(material_id)
+    def sample(self, wi: torch.Tensor, material_id: torch.Tensor = None, *, plan=None, x0=None, seed=None, offset=0,
+               first_index=0):
+        """wi [N,3], material_id [N] (or a ``plan``) -> (wo [N,3], pdf [N]) in wavefront order."""
+        plan = plan if plan is not None else self.plan(material_id)
+        return ops.sample_multi(wi, plan, self.table, self.T, epilogue=self.epilogue, x0=x0, seed=seed, offset=offset,
+                                first_index=first_index, precision=self.precision, fixup=self.fixup)
+
+    def pdf(self, wi: torch.Tensor, wo: torch.Tensor, material_id: torch.Tensor = None, *, plan=None) -> torch.Tensor:
+        plan = plan if plan is not None else self.plan(material_id)
+        return ops.pdf_multi(wo, wi, plan, self.table, self.T, epilogue=self.epilogue, precision=self.precision,
+                             fixup=self.fixup)
+
+    def sample_per_material(self, wi: torch.Tensor, material_id: torch.Tensor, *, x0=None, seed=None, offset=0,
+                            first_index=0):
+        """The dispatch Mitsuba performs (one call per instance over the lanes that hit it), kept as the A/B partner of
+        the single launch: boolean-mask gather, one launch per material, scatter.  Philox counters here are positions
+        inside each bucket, so the base samples differ from ``sample`` unless ``x0`` is replayed."""
         if x0 is None and seed is None:
-            seed, offset = ops.next_philox(wi.device)       # one draw from torch's generator for the whole wavefront
-        wi_s = wi.index_select(0, order)
-        x0_s = x0.index_select(0, order) if x0 is not None else None
-        wo_s = torch.empty_like(wi_s)
-        pdf_s = torch.empty(wi_s.shape[0], dtype=torch.float32, device=wi.device)
-        a = 0
-        for m, c in enumerate(counts):
-            if c:
-                s = self.samplers[m]
-                ops.sample_into(wi_s[a:a + c], s.flow, s.base, s.T, wo_s[a:a + c], pdf_s[a:a + c],
-                                epilogue=s.epilogue, x0=None if x0_s is None else x0_s[a:a + c], seed=seed,
-                                offset=offset, first_index=first_index + a, precision=s.precision, fixup=s.fixup,
-                                scratch=torch.empty(ops.sample_scratch_elems(c), dtype=torch.int32, device=wi.device))
-            a += c
-        wo = torch.empty_like(wo_s)
-        pdf = torch.empty_like(pdf_s)
-        wo.index_copy_(0, order, wo_s)
-        pdf.index_copy_(0, order, pdf_s)
+            seed, offset = ops.next_philox(wi.device)
+        wo = torch.zeros_like(wi)
+        pdf = torch.zeros(wi.shape[0], dtype=torch.float32, device=wi.device)
+        for m, s in enumerate(self.samplers):
+            rows = (material_id == m).nonzero(as_tuple=True)[0]          # host sync: the bucket size
+            if rows.numel():
+                w, p = s.sample(wi.index_select(0, rows), x0=None if x0 is None else x0.index_select(0, rows), seed=seed,
+                                offset=offset, first_index=first_index)
+                wo.index_copy_(0, rows, w)
+                pdf.index_copy_(0, rows, p)
         return wo, pdf
-
-    def pdf(self, wi: torch.Tensor, wo: torch.Tensor, material_id: torch.Tensor) -> torch.Tensor:
-        order, counts = self._buckets(material_id)
-        wi_s, wo_s = wi.index_select(0, order), wo.index_select(0, order)
-        out_s = torch.empty(wi_s.shape[0], dtype=torch.float32, device=wi.device)
-        a = 0
-        for m, c in enumerate(counts):
-            if c:
-                out_s[a:a + c] = self.samplers[m].pdf(wi_s[a:a + c], wo_s[a:a + c])
-            a += c
-        out = torch.empty_like(out_s)
-        out.index_copy_(0, order, out_s)
-        return out
 
 
 def make_mybsdf(kind: str, checkpoint_root: str = "./checkpoints_new", bsdf_root: str = "./measuredbsdfs",

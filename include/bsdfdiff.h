@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define BSDFDIFF_ABI_VERSION 2
+#define BSDFDIFF_ABI_VERSION 3
 
 /* domains (state parameterisation of the flow) */
 #define BSDFDIFF_DISK       0   /* state = projected (x,y) on the unit disk; net input 25 = [x,y,alpha,PE5(wi)] */
@@ -141,6 +141,35 @@ int bsdfdiff_flow_forward(int precision, int domain, int T, int64_t n, const flo
 /* ---- one MLP forward (tinycudann.Network.forward, inference): out[n,2] = MLP(in[n,in_dim]) ------------------ */
 int bsdfdiff_mlp_forward(int precision, int64_t n, const float* in, int in_dim, const void* flow_packed,
                          int hidden, int n_hidden, float* out /*[n,2]*/, void* cuda_stream);
+
+/* ---- one wavefront, several materials: a material id per row, ONE launch -------------------
+ * Replaces Mitsuba's per-instance dispatch for scenes with many `mybsdf` BSDFs (twelve in
+ * rendering/matpreview/disney_bsdf_array0_envmap.xml:35-335: each instance's sample()/pdf() is called with the lanes
+ * that hit it) for a renderer that keeps one wavefront with a material id per lane.
+ * bsdfdiff_multi_plan buckets the rows by material ON THE DEVICE (histogram, tile table, scatter: no host read) into
+ * virtual tiles of <= 128 rows of one material; bsdfdiff_sample_multi / bsdfdiff_pdf_multi walk that tile table in one
+ * persistent launch and switch the weight set in shared memory per tile (PREC_TC16: one weight image per in-flight
+ * tile, re-staged with one cp.async.bulk when a tile's material differs).  Rows are read and written at their
+ * WAVEFRONT position and the Philox counter is first_index + wavefront row, so every row equals the single-material
+ * call on that row bit for bit, whatever the bucketing.  Rows whose id is outside [0, n_materials) are inactive lanes:
+ * no flow runs for them and their outputs are zeroed.  A plan can be reused by any number of sample / pdf calls on the
+ * same material_id column (sample, then pdf for MIS); calls sharing one plan must be stream-ordered.
+ * material_id:   [n] int32 (device).   scratch / plan: device buffer of bsdfdiff_multi_scratch_bytes(n, n_materials).
+ * flows_packed:  DEVICE array [n_materials] of device pointers to packed flow blobs, all of one (domain, hidden,
+ *                n_hidden) shape;  base_params: DEVICE array [n_materials] of device pointers to 308-float base blobs.
+ * fix_threshold: as bsdfdiff_sample (the plan buffer holds the per-material fix-up lists and, when neither x0_replay
+ *                nor out_x0 is given, the base samples the fix-up pass replays).  n_materials <= 255, n < 2^31. */
+size_t bsdfdiff_multi_scratch_bytes(int64_t n, int n_materials);
+int bsdfdiff_multi_plan(int64_t n, const int32_t* material_id, int n_materials, void* scratch, void* cuda_stream);
+int bsdfdiff_sample_multi(int precision, int domain, int epilogue, int T, int64_t n, const float* wi,
+                          const void* plan, int n_materials, const void* const* flows_packed,
+                          const float* const* base_params, int hidden, int n_hidden, const float* x0_replay,
+                          uint64_t seed, uint64_t offset, int64_t first_index, float* out_dir, float* out_pdf,
+                          float* out_x0, float fix_threshold, void* cuda_stream);
+int bsdfdiff_pdf_multi(int precision, int domain, int epilogue, int T, int64_t n, const float* wo, const float* wi,
+                       const void* plan, int n_materials, const void* const* flows_packed,
+                       const float* const* base_params, int hidden, int n_hidden, float* out_pdf,
+                       float fix_threshold, void* cuda_stream);
 
 /* ---- measured-BSDF ground truth: Mitsuba 3 `measured` eval of an RGL tensor file, and the plugins' weight + firefly clamp ----
  * Replaces  self.bsdf.eval(ctx, si, bs.wo)  (mi.load_dict({"type": "measured", ...}), rendering/brdf_measured_disk.py:36-42,92

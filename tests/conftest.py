@@ -26,7 +26,11 @@ def golden_ids():
 @pytest.fixture(scope="session")
 def built_lib():
     """Build libbsdfdiff.so if needed (nvcc cross-compiles on CPU) and return the package."""
-    from bsdf_diffusion_sampling_b200 import build as _build
+    # build.py is loaded by file path: importing the package itself requires an up-to-date library
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bsdfdiff_build", os.path.join(ROOT, "bsdf_diffusion_sampling_b200", "build.py"))
+    _build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(_build)
     _build.build()
     import bsdf_diffusion_sampling_b200 as pkg
     return pkg

@@ -436,37 +436,100 @@ def test_cuda_graph_capture(pkg, prec):
     torch.cuda.synchronize()
 
 
-def test_multi_material_wavefront(pkg):
-    """One wavefront with a material id per lane == the per-material calls on the lanes of each material."""
+def _material_set(pkg, kind, tag, T=None, precision=None):
+    files = [f for f in GOLDEN_FILES if f.replace("\\", "/").split("/")[-1].startswith(tag)]
     mats = []
-    disk_files = [f for f in GOLDEN_FILES if "disk_" in f.replace("\\", "/").split("/")[-1]]
-    assert len(disk_files) == 3
-    for path in disk_files:
+    for path in files:
         flow, base, _ = O.load_material_npz(path)
-        mats.append(pkg.plugins.NeuralBSDFSampler("disk", pkg.weights.pack_flow_layers(flow.layers, "cuda"),
-                                                  pkg.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, "cuda")))
+        mats.append(pkg.plugins.NeuralBSDFSampler(kind, pkg.weights.pack_flow_layers(flow.layers, "cuda"),
+                                                  pkg.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, "cuda"),
+                                                  T=T, precision=precision))
+    return mats
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("kind,tag", [("disk", "disk_"), ("spherical", "spherical_"), ("bsdf", "bsdf_")])
+def test_multi_material_single_launch(pkg, kind, tag, prec):
+    """One wavefront with a material id per row, ONE launch (device-side bucketing, weight set switched per 128-row
+    tile): row i equals the single-material call of material id[i] on the WHOLE wavefront at row i, bit for bit --
+    Philox draws included, since the counter is the wavefront row.  Inactive rows (id outside the table) are zeroed."""
+    mats = _material_set(pkg, kind, tag, precision=prec)
+    assert len(mats) >= 2
+    M = len(mats)
     mm = pkg.plugins.MultiMaterialSampler(mats)
     rng = np.random.default_rng(5)
-    n = 50_000
+    n = 50_001
     w = rng.normal(size=(n, 3)).astype(np.float32)
-    w[:, 2] = np.abs(w[:, 2]) + 0.05
+    if kind != "bsdf":
+        w[:, 2] = np.abs(w[:, 2]) + 0.05
     wi = cu(w / np.linalg.norm(w, axis=1, keepdims=True))
-    x0 = cu(rng.normal(0, 0.3, (n, 2)).astype(np.float32))
-    mid = torch.from_numpy(rng.integers(0, 3, n)).cuda()
-    mid[:7] = 1                                            # a run of equal ids at the front
-    wo, pdf = mm.sample(wi, mid, x0=x0)
-    p2 = mm.pdf(wi, wo, mid)
+    ids = rng.integers(0, M, n)
+    ids[:300] = 1                                          # a run of equal ids at the front
+    ids[rng.integers(0, n, 500)] = -1                      # inactive lanes
+    ids[rng.integers(0, n, 50)] = M + 3
+    mid = torch.from_numpy(ids.astype(np.int32)).cuda()
+    plan = mm.plan(mid)
+    counts = plan.counts().cpu().numpy()
+    assert counts[:M].tolist() == [int((ids == m).sum()) for m in range(M)]
+    assert counts[M] == int(((ids < 0) | (ids >= M)).sum())
+    # the plan is a permutation of the rows, each material's rows contiguous
+    perm_off = 1280 + 4 * (n // 128 + M + 1)
+    perm = plan.scratch[perm_off:perm_off + n].cpu().numpy()
+    assert np.array_equal(np.sort(perm), np.arange(n))
+    seg = np.concatenate([[0], np.cumsum(counts)])
+    for m in range(M):
+        assert (ids[perm[seg[m]:seg[m + 1]]] == m).all()
+
+    wo, pdf = mm.sample(wi, plan=plan, seed=11, offset=40, first_index=1000)
+    p2 = mm.pdf(wi, wo, plan=plan)                         # the same plan serves the pdf() call of the bounce
+    inactive = torch.from_numpy((ids < 0) | (ids >= M)).cuda()
+    assert (wo[inactive] == 0).all() and (pdf[inactive] == 0).all() and (p2[inactive] == 0).all()
     for m, s in enumerate(mats):
         sel = (mid == m).nonzero().squeeze(1)
-        wo_m, pdf_m = s.sample(wi[sel], x0=x0[sel])
-        assert torch.equal(wo[sel], wo_m) and torch.equal(pdf[sel], pdf_m)
-        assert torch.equal(p2[sel], s.pdf(wi[sel], wo_m))
-    # Philox path: deterministic for a given (seed, offset, ids); an id outside the table raises
-    a = mm.sample(wi, mid, seed=3, offset=8)
-    b = mm.sample(wi, mid, seed=3, offset=8)
+        wo_m, pdf_m = s.sample(wi, seed=11, offset=40, first_index=1000)
+        assert torch.equal(wo[sel], wo_m[sel]) and torch.equal(pdf[sel], pdf_m[sel]), f"material {m}"
+        assert torch.equal(p2[sel], s.pdf(wi, wo)[sel]), f"material {m} pdf()"
+    assert torch.isfinite(pdf).all()
+    # replayed base samples, and the plan built implicitly from the id column
+    x0 = cu(rng.normal(0.3, 0.3, (n, 2)).astype(np.float32))
+    wo_r, pdf_r = mm.sample(wi, mid, x0=x0)
+    for m, s in enumerate(mats):
+        sel = (mid == m).nonzero().squeeze(1)
+        wo_m, pdf_m = s.sample(wi, x0=x0)
+        assert torch.equal(wo_r[sel], wo_m[sel]) and torch.equal(pdf_r[sel], pdf_m[sel])
+    # the per-instance dispatch (what Mitsuba does) agrees when the noise is replayed
+    wo_p, pdf_p = mm.sample_per_material(wi, mid, x0=x0)
+    act = ~inactive
+    assert torch.equal(wo_p[act], wo_r[act]) and torch.equal(pdf_p[act], pdf_r[act])
+    if prec == "tc16":
+        print(f"[multi {kind}] fix-up rows per material: {plan.fixup_counts().cpu().tolist()}")
+
+
+def test_multi_material_edge_shapes(pkg):
+    """Tiny wavefronts, a single material in the table, materials with no rows, all lanes inactive."""
+    mats = _material_set(pkg, "disk", "disk_")
+    mm = pkg.plugins.MultiMaterialSampler(mats)
+    rng = np.random.default_rng(9)
+    for n, ids in ((1, [2]), (5, [0, 0, 0, 0, 0]), (129, [1] * 128 + [2]), (300, [-1] * 300)):
+        w = rng.normal(size=(n, 3)).astype(np.float32)
+        w[:, 2] = np.abs(w[:, 2]) + 0.05
+        wi = cu(w / np.linalg.norm(w, axis=1, keepdims=True))
+        mid = torch.tensor(ids, dtype=torch.int64).cuda()
+        wo, pdf = mm.sample(wi, mid, seed=2, offset=4)
+        for m, s in enumerate(mats):
+            sel = (mid == m).nonzero().squeeze(1)
+            if sel.numel():
+                wo_m, pdf_m = s.sample(wi, seed=2, offset=4)
+                assert torch.equal(wo[sel], wo_m[sel]) and torch.equal(pdf[sel], pdf_m[sel])
+        if ids[0] < 0:
+            assert (wo == 0).all() and (pdf == 0).all()
+    one = pkg.plugins.MultiMaterialSampler(mats[:1])
+    wi = cu(np.tile(np.array([[0.3, -0.2, 0.93]], np.float32), (1000, 1)))
+    a = one.sample(wi, torch.zeros(1000, dtype=torch.int32).cuda(), seed=1)
+    b = mats[0].sample(wi, seed=1)
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
-    with pytest.raises(IndexError):
-        mm.sample(wi, mid + 1, seed=3)
+    with pytest.raises(ValueError, match="plan was built for"):
+        one.sample(wi[:10], plan=one.plan(torch.zeros(1000, dtype=torch.int32).cuda()))
 
 
 def test_checkpoint_loading_and_plugin_helpers(pkg, tmp_path):

@@ -22,7 +22,7 @@ def test_every_declared_symbol_is_exported(built_lib):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/bsdfdiff.h but not exported"
     assert set(built_lib._lib.EXPORTS) == declared
-    assert built_lib._lib.lib.bsdfdiff_abi_version() == 2
+    assert built_lib._lib.lib.bsdfdiff_abi_version() == 3
     assert built_lib._lib.lib.bsdfdiff_error_string(-2).decode().startswith("shape not supported")
 
 
@@ -124,29 +124,31 @@ def test_argument_validation_without_gpu(built_lib):
         cp("nope", "m")
 
 
-def test_multi_material_bucketing_without_gpu(built_lib):
-    """MultiMaterialSampler host logic: stable bucket order, counts, id range and kind checks (no kernel call)."""
+def test_multi_material_host_checks_without_gpu(built_lib):
+    """MultiMaterialSampler / ops.MaterialTable host logic: shape, kind, T checks and the scratch-size formula
+    (no kernel call)."""
     P = built_lib.plugins
     flow, base, _ = O.load_material_npz(DISK_FILE)
     pf = built_lib.weights.pack_flow_layers(flow.layers, "cpu")
     pb = built_lib.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, "cpu")
     a, b = P.NeuralBSDFSampler("disk", pf, pb), P.NeuralBSDFSampler("disk", pf, pb, T=8)
-    mm = P.MultiMaterialSampler([a, b])
-    mid = torch.tensor([1, 0, 1, 1, 0, 0, 1], dtype=torch.int32)
-    order, counts = mm._buckets(mid)
-    assert counts == [3, 4]
-    assert order.tolist() == [1, 4, 5, 0, 2, 3, 6]                   # stable: wavefront order inside each bucket
-    with pytest.raises(IndexError):
-        mm._buckets(torch.tensor([0, 2]))
-    with pytest.raises(TypeError):
-        mm._buckets(torch.tensor([0.0, 1.0]))
+    mm = P.MultiMaterialSampler([a, a])
+    assert len(mm.table) == 2 and mm.table.flow_ptrs.tolist() == [pf.blob.data_ptr()] * 2 and mm.T == 4
+    with pytest.raises(ValueError, match="share plugin kind, T"):
+        P.MultiMaterialSampler([a, b])
     with pytest.raises(ValueError):
         P.MultiMaterialSampler([])
     sflow, sbase, _ = O.load_material_npz(BSDF_FILE)
     sph = P.NeuralBSDFSampler("bsdf", built_lib.weights.pack_flow_layers(sflow.layers, "cpu"),
                               built_lib.weights.pack_base_arrays(sbase.w1, sbase.b1, sbase.wo, sbase.bo, "cpu"))
-    with pytest.raises(ValueError, match="share a plugin kind"):
+    with pytest.raises(ValueError, match="share plugin kind"):
         P.MultiMaterialSampler([a, sph])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        mm.plan(torch.tensor([0, 1, 0], dtype=torch.int32))
+    L = built_lib._lib.lib
+    n, M = 1000, 12
+    assert L.bsdfdiff_multi_scratch_bytes(n, M) == 4 * 1280 + 16 * (n // 128 + M + 1) + 8 * n + 8 * n
+    assert L.bsdfdiff_multi_scratch_bytes(n, 0) == 0 and L.bsdfdiff_multi_scratch_bytes(n, 256) == 0
 
 
 def test_model_classes_load_reference_state_dict_keys(built_lib):
