@@ -176,29 +176,33 @@ template <int BACKOFF_NS = 0>
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (BACKOFF_NS > 0) {
         asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+            "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
             "mov.u32 n, 0x400000;\n"
             "WAIT_%=:\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-            "@p bra DONE_%=;\n\t"
+            "vote.sync.all.pred q, p, 0xffffffff;\n\t"
+            "@q bra.uni DONE_%=;\n\t"
             "nanosleep.u32 %5;\n\t"
             "sub.u32 n, n, 1;\n\t"
             "setp.ne.u32 p, n, 0;\n\t"
-            "@p bra WAIT_%=;\n\t"
+            "@p bra.uni WAIT_%=;\n\t"
             "st.global.u32 [%3], %4;\n\t"
             "trap;\n"
             "DONE_%=:\n\t}"
             :: "r"(bar), "r"(parity), "r"(20000u), "l"(&g_tc_timeout_flag), "r"(1u), "n"(BACKOFF_NS) : "memory");
     } else {
+        // (the exit branch goes through a warp vote: ptxas then knows the loop is warp-uniform and keeps the TMEM / barrier
+        // addresses of the surrounding code in uniform registers instead of re-deriving them with R2UR at every use)
         asm volatile(
-            "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+            "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\t"
             "mov.u32 n, 0x400000;\n"
             "WAIT_%=:\n\t"
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-            "@p bra DONE_%=;\n\t"
+            "vote.sync.all.pred q, p, 0xffffffff;\n\t"
+            "@q bra.uni DONE_%=;\n\t"
             "sub.u32 n, n, 1;\n\t"
             "setp.ne.u32 p, n, 0;\n\t"
-            "@p bra WAIT_%=;\n\t"
+            "@p bra.uni WAIT_%=;\n\t"
             "st.global.u32 [%3], %4;\n\t"
             "trap;\n"
             "DONE_%=:\n\t}"
@@ -832,7 +836,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
     // warp index through a shuffle so the compiler can prove it warp-uniform: TMEM addresses and MMA
     // descriptors then live in uniform registers (no per-MMA R2UR/ELECT waterfall)
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int warp = (int)__reduce_max_sync(0xffffffffu, (unsigned)(threadIdx.x >> 5)), lane = threadIdx.x & 31;
     const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(MULTI ? P.flows[0] : P.flow);   // multi: all blobs share one shape
     const int NH = P.n_hidden;
     const uint32_t img_bytes = (hdr->f16_bytes + 127u) & ~127u;                  // multi: one weight image per group
@@ -872,7 +876,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = __shfl_sync(0xffffffffu, S.tmem_base, 0);
+    const uint32_t tmem_base = __reduce_max_sync(0xffffffffu, S.tmem_base);
 
     const long long n_tiles = MULTI ? (long long)*P.n_tiles_dev : (P.n + kTile - 1) / kTile;
     // tile list of this CTA: blockIdx.x, +gridDim.x, ...; entry k goes to group k % kGroups through slot k % kSlots
