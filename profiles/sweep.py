@@ -4,7 +4,7 @@ events, best of 3 after a warm-up), reported as queries/s and as a fraction of t
 algorithmic FLOPs of SURVEY 8(d) scaled to T.  One GPU per process; under torchrun every rank runs the same sweep
 on its own shard (weak scaling, no collective) and rank 0 prints the max-over-ranks time.
 
-    python profiles/sweep.py [--workload disk|spherical] [--n 1,4,16,64] [--T 4,8,32,128,256]
+    python profiles/sweep.py [--workload disk|spherical] [--mq 1,4,16,64] [--T 4,8,32,128,256]
 """
 import argparse
 import json
@@ -23,7 +23,7 @@ import bsdf_diffusion_sampling_b200 as pkg      # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="disk", choices=["disk", "spherical"])
-    ap.add_argument("--n", default="1,4,16,64", help="millions of queries per GPU")
+    ap.add_argument("--mq", "--n", dest="n", default="1,4,16,64", help="millions of queries per GPU (--mq under torchrun: its parser claims --n)")
     ap.add_argument("--T", default="4,8,32,128,256")
     ap.add_argument("--budget-gflop", type=float, default=6.0e5, help="skip cells above this many GFLOP per launch")
     args = ap.parse_args()
