@@ -27,6 +27,7 @@ EXPORTS = [
     "bsdfdiff_sample", "bsdfdiff_pdf", "bsdfdiff_base_log_prob", "bsdfdiff_flow_forward", "bsdfdiff_mlp_forward",
     "bsdfdiff_measured_blob_bytes", "bsdfdiff_measured_pack", "bsdfdiff_measured_eval", "bsdfdiff_measured_weight",
     "bsdfdiff_multi_scratch_bytes", "bsdfdiff_multi_plan", "bsdfdiff_sample_multi", "bsdfdiff_pdf_multi",
+    "bsdfdiff_sample_planar", "bsdfdiff_pdf_planar",
 ]
 
 _c = ctypes
@@ -52,7 +53,7 @@ def _load() -> ctypes.CDLL:
     lib.bsdfdiff_pack_flow_tcnn.argtypes = [_vp, _i, _i, _i, _i, _vp]
     lib.bsdfdiff_fixup_scratch_bytes.restype = _c.c_size_t
     lib.bsdfdiff_fixup_scratch_bytes.argtypes = [_i64]
-    lib.bsdfdiff_sample.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _u64, _u64, _i64,
+    lib.bsdfdiff_sample.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _i, _i, _vp, _vp, _vp, _u64, _u64, _i64,
                                     _vp, _vp, _vp, _f, _vp, _vp]
     lib.bsdfdiff_pdf.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _i, _vp, _vp, _f, _vp, _vp]
     lib.bsdfdiff_base_log_prob.argtypes = [_i, _i64, _vp, _vp, _vp, _vp, _vp]
@@ -67,10 +68,15 @@ def _load() -> ctypes.CDLL:
     lib.bsdfdiff_multi_scratch_bytes.restype = _c.c_size_t
     lib.bsdfdiff_multi_scratch_bytes.argtypes = [_i64, _i]
     lib.bsdfdiff_multi_plan.argtypes = [_i64, _vp, _i, _vp, _vp]
-    lib.bsdfdiff_sample_multi.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _u64, _u64, _i64,
+    lib.bsdfdiff_sample_multi.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _vp, _u64, _u64, _i64,
                                           _vp, _vp, _vp, _f, _vp]
     lib.bsdfdiff_pdf_multi.argtypes = [_i, _i, _i, _i, _i64, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _vp, _f, _vp]
-    for name in ("bsdfdiff_multi_plan", "bsdfdiff_sample_multi", "bsdfdiff_pdf_multi"):
+    _p3 = _c.POINTER(_vp)
+    lib.bsdfdiff_sample_planar.argtypes = [_i, _i, _i, _i, _i64, _p3, _vp, _i, _i, _vp, _vp, _vp, _u64, _u64, _i64,
+                                           _p3, _vp, _vp, _f, _vp, _vp]
+    lib.bsdfdiff_pdf_planar.argtypes = [_i, _i, _i, _i, _i64, _p3, _p3, _vp, _i, _i, _vp, _vp, _f, _vp, _vp]
+    for name in ("bsdfdiff_multi_plan", "bsdfdiff_sample_multi", "bsdfdiff_pdf_multi", "bsdfdiff_sample_planar",
+                 "bsdfdiff_pdf_planar"):
         getattr(lib, name).restype = _i
     for name in ("bsdfdiff_measured_pack", "bsdfdiff_measured_eval", "bsdfdiff_measured_weight"):
         getattr(lib, name).restype = _i

@@ -226,7 +226,7 @@ static int dispatch_fixup(int precision, FlowParams P, cudaStream_t stream, floa
     if (rc != BSDFDIFF_OK) return rc;               // errors, and the fp32 reroute (nothing left to fix)
     FlowParams Q = P;
     Q.fix_pass = 1;
-    if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; }
+    if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; Q.u_noise = nullptr; }
     rc = launch_simt(Q, stream);
     if (rc == -3) return fail_cuda();
     return rc;
@@ -236,6 +236,9 @@ extern "C" size_t bsdfdiff_fixup_scratch_bytes(int64_t n) { return n < 0 ? 0 : 1
 
 static int fill_shape(FlowParams& P, const void* flow_packed, int domain, int hidden, int n_hidden) {
     if ((hidden != 32 && hidden != 64) || n_hidden < 1 || n_hidden > 16) return BSDFDIFF_EUNSUPPORTED;
+    if (P.wi_l.rs == 0) P.wi_l = Dir3Layout{3, 1, 2};                 // interleaved [n,3] unless the caller said otherwise
+    if (P.wo_l.rs == 0) P.wo_l = Dir3Layout{3, 1, 2};
+    if (P.out_l.rs == 0) P.out_l = Dir3Layout{3, 1, 2};
     P.in_dim = (domain == kDisk) ? 25 : 26; P.hidden = hidden; P.n_hidden = n_hidden;
     P.flow = static_cast<const unsigned char*>(flow_packed);
     return 0;
@@ -243,9 +246,9 @@ static int fill_shape(FlowParams& P, const void* flow_packed, int domain, int hi
 
 extern "C" int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
                                const float* wi, const void* flow_packed, int hidden, int n_hidden,
-                               const float* base_params, const float* x0_replay, uint64_t seed, uint64_t offset, int64_t first_index,
-                               float* out_dir, float* out_pdf, float* out_x0, float fix_threshold, void* fix_scratch,
-                               void* cuda_stream) {
+                               const float* base_params, const float* x0_replay, const float* u_noise, uint64_t seed, uint64_t offset,
+                               int64_t first_index, float* out_dir, float* out_pdf, float* out_x0, float fix_threshold,
+                               void* fix_scratch, void* cuda_stream) {
     // T == 0 with flow_packed == NULL evaluates the base distribution alone (D_base.sample / log_prob)
     if (n < 0 || T < 0 || ((T == 0) != (flow_packed == nullptr)) || !base_params ||
         (domain != kDisk && domain != kSpherical) ||
@@ -253,11 +256,11 @@ extern "C" int bsdfdiff_sample(int precision, int domain, int epilogue, int T, i
         (epilogue >= kEpiSpherical && domain != kSpherical))
         return BSDFDIFF_EINVAL;
     if (n == 0) return BSDFDIFF_OK;
-    if (!wi || !out_dir || !out_pdf) return BSDFDIFF_EINVAL;
+    if (!wi || !out_dir || !out_pdf || (x0_replay && u_noise)) return BSDFDIFF_EINVAL;
     cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
     FlowParams P{};
     P.domain = domain; P.mode = kModeSample; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
-    P.wi = wi; P.x0 = x0_replay; P.base = base_params; P.seed = seed; P.offset = offset; P.first_index = first_index;
+    P.wi = wi; P.x0 = x0_replay; P.u_noise = u_noise; P.base = base_params; P.seed = seed; P.offset = offset; P.first_index = first_index;
     P.out_dir = out_dir; P.out_pdf = out_pdf; P.out_x0 = out_x0;
     int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
     if (rc) return rc;
@@ -370,7 +373,7 @@ static int dispatch_multi(int precision, FlowParams P, int n_materials, const vo
     } else if (fix && rc == 0) {
         FlowParams Q = P;
         Q.fix_pass = 1;
-        if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; }
+        if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; Q.u_noise = nullptr; }
         rc = launch_simt(Q, stream);
     }
     if (rc == -3) return fail_cuda();
@@ -390,14 +393,14 @@ static bool bad_domain_epilogue(int domain, int epilogue) {
 extern "C" int bsdfdiff_sample_multi(int precision, int domain, int epilogue, int T, int64_t n, const float* wi,
                                      const void* plan, int n_materials, const void* const* flows_packed,
                                      const float* const* base_params, int hidden, int n_hidden, const float* x0_replay,
-                                     uint64_t seed, uint64_t offset, int64_t first_index, float* out_dir, float* out_pdf,
-                                     float* out_x0, float fix_threshold, void* cuda_stream) {
+                                     const float* u_noise, uint64_t seed, uint64_t offset, int64_t first_index,
+                                     float* out_dir, float* out_pdf, float* out_x0, float fix_threshold, void* cuda_stream) {
     if (n < 0 || T < 1 || bad_domain_epilogue(domain, epilogue)) return BSDFDIFF_EINVAL;
     if (n == 0) return BSDFDIFF_OK;
-    if (!wi || !out_dir || !out_pdf) return BSDFDIFF_EINVAL;
+    if (!wi || !out_dir || !out_pdf || (x0_replay && u_noise)) return BSDFDIFF_EINVAL;
     FlowParams P{};
     P.domain = domain; P.mode = kModeSample; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
-    P.wi = wi; P.x0 = x0_replay; P.seed = seed; P.offset = offset; P.first_index = first_index;
+    P.wi = wi; P.x0 = x0_replay; P.u_noise = u_noise; P.seed = seed; P.offset = offset; P.first_index = first_index;
     P.out_dir = out_dir; P.out_pdf = out_pdf; P.out_x0 = out_x0;
     int rc = fill_shape(P, nullptr, domain, hidden, n_hidden);
     if (rc) return rc;
@@ -419,4 +422,47 @@ extern "C" int bsdfdiff_pdf_multi(int precision, int domain, int epilogue, int T
     if (rc) return rc;
     return dispatch_multi(precision, P, n_materials, flows_packed, base_params, const_cast<void*>(plan), fix_threshold,
                           static_cast<cudaStream_t>(cuda_stream));
+}
+
+// ------------------------------------------------------------------------------------------------
+// planar directions: three separate component arrays per tensor (Dr.Jit Vector3f through DLPack, zero copy)
+// ------------------------------------------------------------------------------------------------
+static bool planar(const float* const c[3], Dir3Layout& l) {
+    if (!c || !c[0] || !c[1] || !c[2]) return false;
+    l = Dir3Layout{1, (long long)(c[1] - c[0]), (long long)(c[2] - c[0])};
+    return true;
+}
+
+extern "C" int bsdfdiff_sample_planar(int precision, int domain, int epilogue, int T, int64_t n, const float* const wi_xyz[3],
+                                      const void* flow_packed, int hidden, int n_hidden, const float* base_params,
+                                      const float* x0_replay, const float* u_noise, uint64_t seed, uint64_t offset,
+                                      int64_t first_index, float* const out_xyz[3], float* out_pdf, float* out_x0,
+                                      float fix_threshold, void* fix_scratch, void* cuda_stream) {
+    if (n < 0 || T < 1 || !flow_packed || !base_params || epilogue == kEpiRaw || bad_domain_epilogue(domain, epilogue))
+        return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    FlowParams P{};
+    if (!planar(wi_xyz, P.wi_l) || !planar(out_xyz, P.out_l) || !out_pdf || (x0_replay && u_noise)) return BSDFDIFF_EINVAL;
+    P.domain = domain; P.mode = kModeSample; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
+    P.wi = wi_xyz[0]; P.x0 = x0_replay; P.u_noise = u_noise; P.base = base_params; P.seed = seed; P.offset = offset;
+    P.first_index = first_index; P.out_dir = out_xyz[0]; P.out_pdf = out_pdf; P.out_x0 = out_x0;
+    int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
+    if (rc) return rc;
+    return dispatch_fixup(precision, P, static_cast<cudaStream_t>(cuda_stream), fix_threshold, fix_scratch);
+}
+
+extern "C" int bsdfdiff_pdf_planar(int precision, int domain, int epilogue, int T, int64_t n, const float* const wo_xyz[3],
+                                   const float* const wi_xyz[3], const void* flow_packed, int hidden, int n_hidden,
+                                   const float* base_params, float* out_pdf, float fix_threshold, void* fix_scratch,
+                                   void* cuda_stream) {
+    if (n < 0 || T < 1 || !flow_packed || !base_params || epilogue == kEpiRaw || bad_domain_epilogue(domain, epilogue))
+        return BSDFDIFF_EINVAL;
+    if (n == 0) return BSDFDIFF_OK;
+    FlowParams P{};
+    if (!planar(wi_xyz, P.wi_l) || !planar(wo_xyz, P.wo_l) || !out_pdf) return BSDFDIFF_EINVAL;
+    P.domain = domain; P.mode = kModePdf; P.epilogue = epilogue; P.T = T; P.n = n; P.wi_repeat = 1;
+    P.wi = wi_xyz[0]; P.wo = wo_xyz[0]; P.base = base_params; P.out_pdf = out_pdf;
+    int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
+    if (rc) return rc;
+    return dispatch_fixup(precision, P, static_cast<cudaStream_t>(cuda_stream), fix_threshold, fix_scratch);
 }

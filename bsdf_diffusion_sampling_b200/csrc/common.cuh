@@ -58,6 +58,12 @@ __host__ __device__ inline int f16_image_halves(int H, int n_hidden) {
     return 2 * (H * 32 + (n_hidden - 1) * H * H + 16 * H);
 }
 
+// Addressing of a 3-component direction tensor (plugin epilogues): component c of row i lives at
+// base[i * rs + (c == 0 ? 0 : c == 1 ? c1 : c2)] (offsets in floats).  Interleaved [n,3]: {3, 1, 2}.  Planar / three
+// separate arrays (Dr.Jit's Vector3f is three arrays: zero-copy through DLPack): {1, y - x, z - x}.
+struct Dir3Layout {
+    long long rs, c1, c2;
+};
 struct FlowParams {
     int domain, mode, epilogue, T;
     int in_dim, hidden, n_hidden;
@@ -65,7 +71,10 @@ struct FlowParams {
     long long wi_repeat;          // query i reads wi[i / wi_repeat]
     const float* wi;              // [.,2] or [.,3]
     const float* wo;              // pdf mode
+    Dir3Layout wi_l, wo_l, out_l; // layouts of wi / wo / out_dir for the 3-component (plugin) epilogues
     const float* x0;              // replayed base sample / reflow start (may be null)
+    const float* u_noise;         // [n,3] uniforms in [0,1) that replace the Philox draws (Mitsuba's sample2.x, sample2.y, sample1;
+                                  // brdf_measured_disk.py:59 hands them to sample() and the reference ignores them), or null
     const unsigned char* flow;    // packed blob (device)
     const float* base;            // 308 floats (device) or null (forward mode with x0 given)
     unsigned long long seed, offset;
@@ -238,11 +247,29 @@ __device__ __forceinline__ float base_logprob(int domain, const float p[4], floa
 //              rejection, wrapped to [-pi,pi)                          (model.py:299-307, torch von_mises.py)
 //   The proposal parameter r is evaluated with a cancellation-free rearrangement so fp32 suffices
 //   (torch switches to fp64 because its formula cancels for small kappa).
+// Renderer-supplied uniforms as the noise source: (ua, ub) feed the Box-Muller pair directly, and the von Mises
+// rejection rounds (which need an unbounded number of uniforms) draw from Philox keyed by the BITS of the three
+// uniforms -- the base sample is a pure function of the renderer's sample stream.
+__device__ __forceinline__ float clamp_u01(float u) { return fminf(fmaxf(u, 2.9802322e-8f), 0.99999994f); }
+__device__ __forceinline__ void noise_key(const float* u, unsigned long long& seed, unsigned long long& offset) {
+    seed = (unsigned long long)__float_as_uint(u[0]) | ((unsigned long long)__float_as_uint(u[1]) << 32);
+    offset = (unsigned long long)__float_as_uint(u[2]) << 8;
+}
 __device__ __forceinline__ void base_draw(int domain, const float p[4], unsigned long long seed,
-                                          unsigned long long offset, long long index, float& x0, float& x1) {
-    uint4 r4 = philox_draw(seed, offset, index, 0);
+                                          unsigned long long offset, long long index, float& x0, float& x1,
+                                          const float* u = nullptr) {
     float n0, n1;
-    box_muller(r4.x, r4.y, n0, n1);
+    if (u) {
+        const float r = sqrtf(-2.0f * logf(clamp_u01(u[0])));
+        float s, c;
+        sincospif(2.0f * clamp_u01(u[1]), &s, &c);
+        n0 = r * c; n1 = r * s;
+        noise_key(u, seed, offset);
+        index = 0;
+    } else {
+        uint4 r4 = philox_draw(seed, offset, index, 0);
+        box_muller(r4.x, r4.y, n0, n1);
+    }
     if (domain == kDisk) {
         x0 = fmaf(n0, expf(p[2]), p[0]);
         x1 = fmaf(n1, expf(p[3]), p[1]);
@@ -289,7 +316,8 @@ __device__ __forceinline__ void load_wi(const FlowParams& P, long long i, float&
         float2 w = reinterpret_cast<const float2*>(P.wi)[q];
         w0 = w.x; w1 = w.y; wz = 1.0f;
     } else {
-        float a = P.wi[3 * q], b = P.wi[3 * q + 1], c = P.wi[3 * q + 2];
+        const float* w = P.wi + q * P.wi_l.rs;
+        float a = w[0], b = w[P.wi_l.c1], c = w[P.wi_l.c2];
         wz = c;
         if (P.epilogue == kEpiDisk) { w0 = a; w1 = b; }            // brdf_measured_disk.py:66-67
         else cart_to_spher(a, b, c, w0, w1);                        // brdf_measured_spherical.py:76-77
@@ -303,7 +331,8 @@ __device__ __forceinline__ void load_wo(const FlowParams& P, long long i, float&
         float2 w = reinterpret_cast<const float2*>(P.wo)[i];
         x0 = w.x; x1 = w.y; wox = woy = 0.0f; woz = 1.0f;
     } else {
-        wox = P.wo[3 * i]; woy = P.wo[3 * i + 1]; woz = P.wo[3 * i + 2];
+        const float* w = P.wo + i * P.wo_l.rs;
+        wox = w[0]; woy = w[P.wo_l.c1]; woz = w[P.wo_l.c2];
         if (P.epilogue == kEpiDisk) { x0 = wox; x1 = woy; }        // brdf_measured_disk.py:118-120
         else cart_to_spher(wox, woy, woz, x0, x1);                  // brdf_measured_spherical.py:131-133
     }
@@ -334,7 +363,8 @@ __device__ __forceinline__ void store_sample(const FlowParams& P, long long i, f
         ox = cp * st; oy = sp * st; oz = ct;                        // sph_to_dir :31-34
         pdf = pdf * inv_sin_clamped(ox, oy);                        // bsdf_myresult.py:81 (abs is a no-op on a sqrt)
     }
-    P.out_dir[3 * i] = ox; P.out_dir[3 * i + 1] = oy; P.out_dir[3 * i + 2] = oz;
+    float* o = P.out_dir + i * P.out_l.rs;
+    o[0] = ox; o[P.out_l.c1] = oy; o[P.out_l.c2] = oz;
     P.out_pdf[i] = pdf;
 }
 

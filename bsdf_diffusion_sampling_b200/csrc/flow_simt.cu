@@ -155,7 +155,9 @@ __device__ __forceinline__ void simt_row(const FlowParams& P, const float* __res
             float2 t = reinterpret_cast<const float2*>(P.x0)[i];
             x0 = t.x; x1 = t.y;
         } else {
-            base_draw(P.domain, bp, P.seed, P.offset, P.first_index + i, x0, x1);
+            float un[3];
+            if (P.u_noise) { un[0] = P.u_noise[3 * i]; un[1] = P.u_noise[3 * i + 1]; un[2] = P.u_noise[3 * i + 2]; }
+            base_draw(P.domain, bp, P.seed, P.offset, P.first_index + i, x0, x1, P.u_noise ? un : nullptr);
         }
         if (P.out_x0) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
         if (P.mode == kModeSample) p0 = expf(base_logprob(P.domain, bp, x0, x1));

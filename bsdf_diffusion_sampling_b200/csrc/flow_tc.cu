@@ -450,13 +450,21 @@ __device__ __forceinline__ float base_logprob_fast(const float p[4], float x0, f
 }
 template <int DOMAIN>
 __device__ __forceinline__ void base_draw_fast(const float p[4], unsigned long long seed, unsigned long long offset,
-                                               long long index, float& x0, float& x1) {
-    const uint4 r4 = philox_draw(seed, offset, index, 0);
+                                               long long index, float& x0, float& x1, const float* u = nullptr) {
+    float ua, ub;
+    if (u) {                                       // renderer-supplied uniforms (common.cuh: base_draw)
+        ua = clamp_u01(u[0]); ub = clamp_u01(u[1]);
+        noise_key(u, seed, offset);
+        index = 0;
+    } else {
+        const uint4 r4 = philox_draw(seed, offset, index, 0);
+        ua = u01(r4.x); ub = u01(r4.y);
+    }
     float n0, n1;
     {
-        const float r = sqrtf(-2.0f * __logf(u01(r4.x)));
+        const float r = sqrtf(-2.0f * __logf(ua));
         float s, c;
-        __sincosf(6.283185307179586f * u01(r4.y) - 3.141592653589793f, &s, &c);   // argument in (-pi, pi)
+        __sincosf(6.283185307179586f * ub - 3.141592653589793f, &s, &c);   // argument in (-pi, pi)
         n0 = -r * c; n1 = -r * s;
     }
     if (DOMAIN == kDisk) {
@@ -792,7 +800,8 @@ struct Pipe {
 struct RawIn {
     float wa, wb, wc;        // wi: (w0, w1, -) raw epilogue, or the 3 local-frame components
     float oa, ob, oc;        // wo (pdf mode)
-    float r0, r1;            // replayed base sample
+    float r0, r1;            // replayed base sample (or, with r2, the renderer's uniforms)
+    float r2;
 };
 template <int MODE>
 __device__ __forceinline__ void raw_load(const FlowParams& P, long long i, RawIn& r) {
@@ -801,18 +810,22 @@ __device__ __forceinline__ void raw_load(const FlowParams& P, long long i, RawIn
         const float2 w = reinterpret_cast<const float2*>(P.wi)[qi];
         r.wa = w.x; r.wb = w.y; r.wc = 1.0f;
     } else {
-        r.wa = P.wi[3 * qi]; r.wb = P.wi[3 * qi + 1]; r.wc = P.wi[3 * qi + 2];
+        const float* w = P.wi + qi * P.wi_l.rs;
+        r.wa = w[0]; r.wb = w[P.wi_l.c1]; r.wc = w[P.wi_l.c2];
     }
     if (MODE == kModePdf) {
         if (P.epilogue == kEpiRaw) {
             const float2 w = reinterpret_cast<const float2*>(P.wo)[i];
             r.oa = w.x; r.ob = w.y; r.oc = 1.0f;
         } else {
-            r.oa = P.wo[3 * i]; r.ob = P.wo[3 * i + 1]; r.oc = P.wo[3 * i + 2];
+            const float* w = P.wo + i * P.wo_l.rs;
+            r.oa = w[0]; r.ob = w[P.wo_l.c1]; r.oc = w[P.wo_l.c2];
         }
     } else if (P.x0) {
         const float2 t = reinterpret_cast<const float2*>(P.x0)[i];
         r.r0 = t.x; r.r1 = t.y;
+    } else if (P.u_noise) {
+        r.r0 = P.u_noise[3 * i]; r.r1 = P.u_noise[3 * i + 1]; r.r2 = P.u_noise[3 * i + 2];
     }
 }
 
@@ -886,7 +899,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         // =========================== producer ==========================================================
         const int row = (warp - kWGroups * 4) * 32 + lane;
         RawIn cur, nxt;
-        cur.wa = cur.wb = cur.wc = cur.oa = cur.ob = cur.oc = cur.r0 = cur.r1 = 0.0f;
+        cur.wa = cur.wb = cur.wc = cur.oa = cur.ob = cur.oc = cur.r0 = cur.r1 = cur.r2 = 0.0f;
         nxt = cur;
         int mat_n = 0;                                      // material of the tile index_of looked at last
         auto index_of = [&](long long k, bool& valid) {
@@ -940,6 +953,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 else cart_to_spher(cur.oa, cur.ob, cur.oc, x0, x1);                                  // brdf_measured_spherical.py:131-133
             } else {
                 if (P.x0) { x0 = cur.r0; x1 = cur.r1; }
+                else if (P.u_noise) { const float un[3] = {cur.r0, cur.r1, cur.r2}; base_draw_fast<DOMAIN>(bp, 0ull, 0ull, 0, x0, x1, un); }
                 else base_draw_fast<DOMAIN>(bp, P.seed, P.offset, P.first_index + i, x0, x1);
                 if (P.out_x0 && valid) reinterpret_cast<float2*>(P.out_x0)[i] = make_float2(x0, x1);
                 if (MODE == kModeSample) p0 = __expf(base_logprob_fast<DOMAIN>(bp, x0, x1));

@@ -111,7 +111,7 @@ def _fix_scratch(n: int, device: torch.device, precision: int, fix_thr: float, T
 # ------------------------------------------------------------------------------------------------
 @torch.library.custom_op("bsdfdiff::sample", mutates_args=(), device_types="cuda")
 def _sample_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor, x0: Optional[torch.Tensor],
-               precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
+               u: Optional[torch.Tensor], precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
                seed: int, offset: int, first_index: int,
                want_x0: bool, fix_thr: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     n = wi.shape[0]
@@ -124,6 +124,7 @@ def _sample_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.
         rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
                                       flow_blob.data_ptr() if flow_blob is not None else None,
                                       hidden, n_hidden, base.data_ptr(), x0.data_ptr() if x0 is not None else None,
+                                      u.data_ptr() if u is not None else None,
                                       seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(),
                                       out_x0.data_ptr() if need_x0 else None,
                                       fix_thr if scratch is not None else 0.0,
@@ -133,7 +134,7 @@ def _sample_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.
 
 
 @_sample_op.register_fake
-def _(wi, flow_blob, base, x0, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, want_x0,
+def _(wi, flow_blob, base, x0, u, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, want_x0,
       fix_thr):
     n = wi.shape[0]
     return (wi.new_empty((n, 2 if epilogue == EPI_RAW else 3)), wi.new_empty((n,)),
@@ -142,7 +143,7 @@ def _(wi, flow_blob, base, x0, precision, domain, epilogue, T, hidden, n_hidden,
 
 @torch.library.custom_op("bsdfdiff::sample_out", mutates_args=("out_dir", "out_pdf", "scratch"), device_types="cuda")
 def _sample_out_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.Tensor, x0: Optional[torch.Tensor],
-                   out_dir: torch.Tensor, out_pdf: torch.Tensor, scratch: Optional[torch.Tensor],
+                   u: Optional[torch.Tensor], out_dir: torch.Tensor, out_pdf: torch.Tensor, scratch: Optional[torch.Tensor],
                    precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
                    seed: int, offset: int, first_index: int, fix_thr: float) -> None:
     """As ``bsdfdiff::sample`` but writes into caller-owned buffers (no allocation: streaming pipelines).
@@ -156,6 +157,7 @@ def _sample_out_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: to
         rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
                                       flow_blob.data_ptr() if flow_blob is not None else None,
                                       hidden, n_hidden, base.data_ptr(), x0.data_ptr() if x0 is not None else None,
+                                      u.data_ptr() if u is not None else None,
                                       seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(),
                                       x0_side.data_ptr() if x0_side is not None else None,
                                       fix_thr if fix else 0.0, scratch.data_ptr() if fix else None, _stream(wi))
@@ -235,6 +237,102 @@ def _(x, flow_blob, precision, hidden, n_hidden):
     return x.new_empty((x.shape[0], 2))
 
 
+# ---- planar directions (three component arrays per tensor: Dr.Jit Vector3f through DLPack, zero copy) -----------------
+def _ptr3(a: torch.Tensor, b: torch.Tensor, c: torch.Tensor):
+    import ctypes
+    return (ctypes.c_void_p * 3)(a.data_ptr(), b.data_ptr(), c.data_ptr())
+
+
+@torch.library.custom_op("bsdfdiff::sample_planar", mutates_args=(), device_types="cuda")
+def _sample_planar_op(wx: torch.Tensor, wy: torch.Tensor, wz: torch.Tensor, flow_blob: torch.Tensor, base: torch.Tensor,
+                      x0: Optional[torch.Tensor], u: Optional[torch.Tensor], precision: int, domain: int, epilogue: int,
+                      T: int, hidden: int, n_hidden: int, seed: int, offset: int, first_index: int,
+                      fix_thr: float) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+    n = wx.shape[0]
+    ox, oy, oz, pdf = (torch.empty((n,), dtype=torch.float32, device=wx.device) for _ in range(4))
+    scratch = _fix_scratch(n, wx.device, precision, fix_thr, T)
+    side = torch.empty((n if (scratch is not None and x0 is None) else 0, 2), dtype=torch.float32, device=wx.device)
+    with torch.cuda.device(wx.device):
+        rc = _lib.lib.bsdfdiff_sample_planar(precision, domain, epilogue, T, n, _ptr3(wx, wy, wz), flow_blob.data_ptr(),
+                                             hidden, n_hidden, base.data_ptr(),
+                                             x0.data_ptr() if x0 is not None else None,
+                                             u.data_ptr() if u is not None else None, seed, offset, first_index,
+                                             _ptr3(ox, oy, oz), pdf.data_ptr(), side.data_ptr() if side.numel() else None,
+                                             fix_thr if scratch is not None else 0.0,
+                                             scratch.data_ptr() if scratch is not None else None, _stream(wx))
+    _lib.check(rc, "bsdfdiff_sample_planar")
+    return ox, oy, oz, pdf
+
+
+@_sample_planar_op.register_fake
+def _(wx, wy, wz, flow_blob, base, x0, u, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, fix_thr):
+    return tuple(wx.new_empty((wx.shape[0],)) for _ in range(4))
+
+
+@torch.library.custom_op("bsdfdiff::pdf_planar", mutates_args=(), device_types="cuda")
+def _pdf_planar_op(ox: torch.Tensor, oy: torch.Tensor, oz: torch.Tensor, wx: torch.Tensor, wy: torch.Tensor, wz: torch.Tensor,
+                   flow_blob: torch.Tensor, base: torch.Tensor, precision: int, domain: int, epilogue: int, T: int,
+                   hidden: int, n_hidden: int, fix_thr: float) -> torch.Tensor:
+    n = wx.shape[0]
+    out = torch.empty((n,), dtype=torch.float32, device=wx.device)
+    scratch = _fix_scratch(n, wx.device, precision, fix_thr, T)
+    with torch.cuda.device(wx.device):
+        rc = _lib.lib.bsdfdiff_pdf_planar(precision, domain, epilogue, T, n, _ptr3(ox, oy, oz), _ptr3(wx, wy, wz),
+                                          flow_blob.data_ptr(), hidden, n_hidden, base.data_ptr(), out.data_ptr(),
+                                          fix_thr if scratch is not None else 0.0,
+                                          scratch.data_ptr() if scratch is not None else None, _stream(wx))
+    _lib.check(rc, "bsdfdiff_pdf_planar")
+    return out
+
+
+@_pdf_planar_op.register_fake
+def _(ox, oy, oz, wx, wy, wz, flow_blob, base, precision, domain, epilogue, T, hidden, n_hidden, fix_thr):
+    return wx.new_empty((wx.shape[0],))
+
+
+def from_dlpack(obj) -> torch.Tensor:
+    """A torch view of any DLPack exporter (Dr.Jit arrays, CuPy, JAX, ...) without a copy; torch tensors pass through."""
+    return obj if isinstance(obj, torch.Tensor) else torch.from_dlpack(obj)
+
+
+def _planar3(comps, what: str):
+    cs = [from_dlpack(c) for c in comps]
+    if len(cs) != 3:
+        raise ValueError(f"bsdfdiff: {what} must be three component arrays")
+    n = cs[0].shape[0]
+    for c in cs:
+        if (not c.is_cuda) or c.dtype != torch.float32 or c.dim() != 1 or c.shape[0] != n or not c.is_contiguous() \
+                or c.device != cs[0].device:
+            raise ValueError(f"bsdfdiff: {what} components must be contiguous 1-D fp32 CUDA arrays of one length on one device")
+    return cs
+
+
+def sample_planar(wi_xyz, flow, base: torch.Tensor, T: int, *, epilogue: int, x0=None, u=None, seed: Optional[int] = None,
+                  offset: int = 0, first_index: int = 0, precision=None, fixup=None):
+    """``sample`` on three component arrays (anything that speaks DLPack) -> (wo_x, wo_y, wo_z, pdf), each [n]."""
+    wx, wy, wz = _planar3(wi_xyz, "wi")
+    if epilogue == EPI_RAW:
+        raise ValueError("planar directions exist for the plugin epilogues only")
+    _check_flow(flow, T, "sample_planar")
+    if T < 1:
+        raise ValueError("T must be >= 1")
+    x0, u, seed, offset = _noise(wx.unsqueeze(1), x0, u, seed, offset)
+    return _sample_planar_op(wx, wy, wz, flow.blob, base, x0, u, _resolve_precision(precision), flow.domain, epilogue,
+                             int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), _fix_thr(fixup))
+
+
+def pdf_planar(wo_xyz, wi_xyz, flow, base: torch.Tensor, T: int, *, epilogue: int, precision=None, fixup=None) -> torch.Tensor:
+    wx, wy, wz = _planar3(wi_xyz, "wi")
+    ox, oy, oz = _planar3(wo_xyz, "wo")
+    if ox.shape[0] != wx.shape[0]:
+        raise ValueError("bsdfdiff: wi and wo must have the same number of rows")
+    if epilogue == EPI_RAW:
+        raise ValueError("planar directions exist for the plugin epilogues only")
+    _check_flow(flow, T, "pdf_planar")
+    return _pdf_planar_op(ox, oy, oz, wx, wy, wz, flow.blob, base, _resolve_precision(precision), flow.domain, epilogue,
+                          int(T), flow.hidden, flow.n_hidden, _fix_thr(fixup))
+
+
 # ---- one wavefront, several materials (include/bsdfdiff.h: bsdfdiff_multi_plan / _sample_multi / _pdf_multi) ----------
 @torch.library.custom_op("bsdfdiff::multi_plan", mutates_args=(), device_types="cuda")
 def _multi_plan_op(material_id: torch.Tensor, n_materials: int) -> torch.Tensor:
@@ -256,7 +354,7 @@ def _(material_id, n_materials):
 
 @torch.library.custom_op("bsdfdiff::sample_multi", mutates_args=("plan",), device_types="cuda")
 def _sample_multi_op(wi: torch.Tensor, plan: torch.Tensor, flows: torch.Tensor, bases: torch.Tensor,
-                     x0: Optional[torch.Tensor], precision: int, domain: int, epilogue: int, T: int, hidden: int,
+                     x0: Optional[torch.Tensor], u: Optional[torch.Tensor], precision: int, domain: int, epilogue: int, T: int, hidden: int,
                      n_hidden: int, seed: int, offset: int, first_index: int,
                      fix_thr: float) -> Tuple[torch.Tensor, torch.Tensor]:
     n = wi.shape[0]
@@ -265,14 +363,15 @@ def _sample_multi_op(wi: torch.Tensor, plan: torch.Tensor, flows: torch.Tensor, 
     with torch.cuda.device(wi.device):
         rc = _lib.lib.bsdfdiff_sample_multi(precision, domain, epilogue, T, n, wi.data_ptr(), plan.data_ptr(),
                                             flows.shape[0], flows.data_ptr(), bases.data_ptr(), hidden, n_hidden,
-                                            x0.data_ptr() if x0 is not None else None, seed, offset, first_index,
+                                            x0.data_ptr() if x0 is not None else None,
+                                            u.data_ptr() if u is not None else None, seed, offset, first_index,
                                             out_dir.data_ptr(), out_pdf.data_ptr(), None, fix_thr, _stream(wi))
     _lib.check(rc, "bsdfdiff_sample_multi")
     return out_dir, out_pdf
 
 
 @_sample_multi_op.register_fake
-def _(wi, plan, flows, bases, x0, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, fix_thr):
+def _(wi, plan, flows, bases, x0, u, precision, domain, epilogue, T, hidden, n_hidden, seed, offset, first_index, fix_thr):
     n = wi.shape[0]
     return wi.new_empty((n, 2 if epilogue == EPI_RAW else 3)), wi.new_empty((n,))
 
@@ -358,20 +457,15 @@ def _check_multi(table: MaterialTable, plan: MultiPlan, wi: torch.Tensor, T: int
 
 
 def sample_multi(wi: torch.Tensor, plan: MultiPlan, table: MaterialTable, T: int, *, epilogue: int = EPI_RAW,
-                 x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0, first_index: int = 0,
-                 precision=None, fixup=None):
+                 x0: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None, seed: Optional[int] = None,
+                 offset: int = 0, first_index: int = 0, precision=None, fixup=None):
     """One launch for a wavefront with a material id per row -> (dir [n,2|3], pdf [n]) in wavefront order."""
     _require_cuda(wi, "sample_multi")
     wi = _f32c(wi)
     _check_rows(wi, wi.shape[0], 2 if epilogue == EPI_RAW else 3, "wi")
     _check_multi(table, plan, wi, T, "sample_multi")
-    if x0 is not None:
-        x0 = _f32c(x0, wi.device)
-        _check_rows(x0, wi.shape[0], 2, "x0")
-        seed, offset = 0, 0
-    elif seed is None:
-        seed, offset = next_philox(wi.device)
-    return _sample_multi_op(wi, plan.scratch, table.flow_ptrs, table.base_ptrs, x0, _resolve_precision(precision),
+    x0, u, seed, offset = _noise(wi, x0, u, seed, offset)
+    return _sample_multi_op(wi, plan.scratch, table.flow_ptrs, table.base_ptrs, x0, u, _resolve_precision(precision),
                             table.domain, epilogue, int(T), table.hidden, table.n_hidden, int(seed), int(offset),
                             int(first_index), _fix_thr(fixup))
 
@@ -418,23 +512,39 @@ def _fix_thr(fixup) -> float:
     return _fixup_threshold if fixup is None else float(fixup)
 
 
+def _noise(wi: torch.Tensor, x0, u, seed, offset):
+    """-> (x0, u, seed, offset): exactly one noise source.  ``x0`` = replayed base samples [n,2]; ``u`` = renderer
+    uniforms [n,3] in [0,1) (Mitsuba's sample2.x, sample2.y, sample1); else Philox (seed, offset), drawn from torch's
+    CUDA generator when no seed is given."""
+    n = wi.shape[0]
+    if x0 is not None and u is not None:
+        raise ValueError("bsdfdiff: pass either x0= (replayed base samples) or u= (renderer uniforms), not both")
+    if x0 is not None:
+        x0 = _f32c(x0, wi.device)
+        _check_rows(x0, n, 2, "x0")
+        return x0, None, 0, 0
+    if u is not None:
+        u = _f32c(u, wi.device)
+        _check_rows(u, n, 3, "u")
+        return None, u, 0, 0
+    if seed is None:
+        seed, offset = next_philox(wi.device)
+    return None, None, int(seed), int(offset)
+
+
 def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,
-           x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0, first_index: int = 0,
-           precision=None, return_x0: bool = True, fixup=None):
+           x0: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0,
+           first_index: int = 0, precision=None, return_x0: bool = True, fixup=None):
     """-> (dir [n,2|3], pdf [n], x0 [n,2]).  ``flow`` is a ``weights.PackedFlow``.
-    ``return_x0=False`` skips returning the base sample; x0 is then empty.  ``fixup`` = conditioning threshold of the
-    fp32 fix-up pass of the tc16 path (None: the module default, 0: off)."""
+    Noise: ``x0=`` replays base samples, ``u=`` [n,3] uses the renderer's uniforms (sample2.x, sample2.y, sample1), else
+    Philox.  ``return_x0=False`` skips returning the base sample; x0 is then empty.  ``fixup`` = conditioning threshold
+    of the fp32 fix-up pass of the tc16 path (None: the module default, 0: off)."""
     _require_cuda(wi, "sample")
     wi = _f32c(wi)
     _check_flow(flow, T, "sample")
     _check_rows(wi, wi.shape[0], 2 if epilogue == EPI_RAW else 3, "wi")
-    if x0 is not None:
-        x0 = _f32c(x0, wi.device)
-        _check_rows(x0, wi.shape[0], 2, "x0")
-        seed, offset = 0, 0
-    elif seed is None:
-        seed, offset = next_philox(wi.device)
-    return _sample_op(wi, flow.blob, base, x0, _resolve_precision(precision), flow.domain, epilogue, int(T),
+    x0, u, seed, offset = _noise(wi, x0, u, seed, offset)
+    return _sample_op(wi, flow.blob, base, x0, u, _resolve_precision(precision), flow.domain, epilogue, int(T),
                       flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), bool(return_x0),
                       _fix_thr(fixup))
 
@@ -445,7 +555,8 @@ def sample_scratch_elems(n: int) -> int:
 
 
 def sample_into(wi: torch.Tensor, flow, base: torch.Tensor, T: int, out_dir: torch.Tensor, out_pdf: torch.Tensor, *,
-                epilogue: int = EPI_RAW, x0: Optional[torch.Tensor] = None, seed: Optional[int] = None, offset: int = 0,
+                epilogue: int = EPI_RAW, x0: Optional[torch.Tensor] = None, u: Optional[torch.Tensor] = None,
+                seed: Optional[int] = None, offset: int = 0,
                 first_index: int = 0, precision=None, scratch: Optional[torch.Tensor] = None, fixup=None) -> None:
     """``sample`` into caller-owned contiguous fp32 CUDA buffers ``out_dir`` [n,2|3] and ``out_pdf`` [n].
     ``scratch``: caller-owned int32 CUDA buffer of ``sample_scratch_elems(n)`` elements; without it the call is the
@@ -462,13 +573,8 @@ def sample_into(wi: torch.Tensor, flow, base: torch.Tensor, T: int, out_dir: tor
         raise ValueError(f"bsdfdiff.sample_into: scratch must be a contiguous int32 CUDA tensor of >= "
                          f"{sample_scratch_elems(n)} elements")
     _check_flow(flow, T, "sample_into")
-    if x0 is not None:
-        x0 = _f32c(x0, wi.device)
-        _check_rows(x0, n, 2, "x0")
-        seed, offset = 0, 0
-    elif seed is None:
-        seed, offset = next_philox(wi.device)
-    _sample_out_op(wi, flow.blob, base, x0, out_dir, out_pdf, scratch, _resolve_precision(precision), flow.domain,
+    x0, u, seed, offset = _noise(wi, x0, u, seed, offset)
+    _sample_out_op(wi, flow.blob, base, x0, u, out_dir, out_pdf, scratch, _resolve_precision(precision), flow.domain,
                    epilogue, int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index),
                    _fix_thr(fixup))
 

@@ -85,9 +85,10 @@ class NeuralBSDFSampler:
         return cls(kind, flow, base, **kw)
 
     # -- the two hot calls ----------------------------------------------------------------------
-    def sample(self, wi: torch.Tensor, *, x0=None, seed=None, offset=0, first_index=0):
-        """wi [N,3] local frame -> (wo [N,3], pdf_omega [N]) == (bs.wo, bs.pdf as first assigned)."""
-        wo, pdf, _ = ops.sample(wi, self.flow, self.base, self.T, epilogue=self.epilogue, x0=x0, seed=seed,
+    def sample(self, wi: torch.Tensor, *, x0=None, u=None, seed=None, offset=0, first_index=0):
+        """wi [N,3] local frame -> (wo [N,3], pdf_omega [N]) == (bs.wo, bs.pdf as first assigned).
+        ``u`` [N,3] = the renderer's uniforms (sample2.x, sample2.y, sample1) as the noise source."""
+        wo, pdf, _ = ops.sample(wi, self.flow, self.base, self.T, epilogue=self.epilogue, x0=x0, u=u, seed=seed,
                                 offset=offset, first_index=first_index, precision=self.precision,
                                 return_x0=False, fixup=self.fixup)
         return wo, pdf
@@ -96,6 +97,16 @@ class NeuralBSDFSampler:
         """(wi [N,3], wo [N,3]) -> pdf_omega [N] (MyBSDF.pdf incl. the cos/sin masks of the plugin kind)."""
         return ops.pdf(wo, wi, self.flow, self.base, self.T, epilogue=self.epilogue, precision=self.precision,
                        fixup=self.fixup)
+
+    def sample_planar(self, wi_xyz, *, x0=None, u=None, seed=None, offset=0, first_index=0):
+        """Zero-copy variant for renderers that keep directions as three arrays (Dr.Jit ``Vector3f``): ``wi_xyz`` = three
+        DLPack-capable [N] arrays -> (wo_x, wo_y, wo_z, pdf_omega) as torch tensors ([N] each; ``mi.Float(t)`` wraps them)."""
+        return ops.sample_planar(wi_xyz, self.flow, self.base, self.T, epilogue=self.epilogue, x0=x0, u=u, seed=seed,
+                                 offset=offset, first_index=first_index, precision=self.precision, fixup=self.fixup)
+
+    def pdf_planar(self, wi_xyz, wo_xyz) -> torch.Tensor:
+        return ops.pdf_planar(wo_xyz, wi_xyz, self.flow, self.base, self.T, epilogue=self.epilogue,
+                              precision=self.precision, fixup=self.fixup)
 
     def sample_weighted(self, wi: torch.Tensor, bsdf: "_measured.MeasuredBSDF", albedo=(1.0, 1.0, 1.0), *, x0=None,
                         seed=None, offset=0, first_index=0):
@@ -218,11 +229,11 @@ class MultiMaterialSampler:
         """Bucket the wavefront once; reuse the plan for ``sample`` and the ``pdf`` calls of the same bounce."""
         return ops.MultiPlan(material_id, len(self.samplers))
 
-    def sample(self, wi: torch.Tensor, material_id: torch.Tensor = None, *, plan=None, x0=None, seed=None, offset=0,
-               first_index=0):
+    def sample(self, wi: torch.Tensor, material_id: torch.Tensor = None, *, plan=None, x0=None, u=None, seed=None,
+               offset=0, first_index=0):
         """wi [N,3], material_id [N] (or a ``plan``) -> (wo [N,3], pdf [N]) in wavefront order."""
         plan = plan if plan is not None else self.plan(material_id)
-        return ops.sample_multi(wi, plan, self.table, self.T, epilogue=self.epilogue, x0=x0, seed=seed, offset=offset,
+        return ops.sample_multi(wi, plan, self.table, self.T, epilogue=self.epilogue, x0=x0, u=u, seed=seed, offset=offset,
                                 first_index=first_index, precision=self.precision, fixup=self.fixup)
 
     def pdf(self, wi: torch.Tensor, wo: torch.Tensor, material_id: torch.Tensor = None, *, plan=None) -> torch.Tensor:
@@ -250,11 +261,16 @@ class MultiMaterialSampler:
 
 
 def make_mybsdf(kind: str, checkpoint_root: str = "./checkpoints_new", bsdf_root: str = "./measuredbsdfs",
-                bsdf_materials=None):
+                bsdf_materials=None, noise: str = "torch"):
     """Return a ``MyBSDF(mi.BSDF)`` class for ``mi.register_bsdf("mybsdf", lambda p: MyBSDF(p))``.
 
     Requires mitsuba + drjit (variant ``cuda_ad_rgb`` already set by the caller).  ``bsdf_materials`` is the
-    ground-truth table the bsdf kind indexes with ``props["idx"]`` (rendering/utils/bsdf_dict.py)."""
+    ground-truth table the bsdf kind indexes with ``props["idx"]`` (rendering/utils/bsdf_dict.py).
+    ``noise="torch"`` draws the base samples from torch's CUDA generator like the reference (which ignores Mitsuba's
+    ``sample1`` / ``sample2``, brdf_measured_disk.py:59-68); ``noise="mitsuba"`` uses ``sample2.x, sample2.y, sample1``
+    as the noise source, so the render is a function of Mitsuba's sampler (seed, stratification) alone."""
+    if noise not in ("torch", "mitsuba"):
+        raise ValueError("noise must be 'torch' or 'mitsuba'")
     import drjit as dr            # noqa: F401  (gated: not available in the build container)
     import mitsuba as mi
 
@@ -280,7 +296,10 @@ def make_mybsdf(kind: str, checkpoint_root: str = "./checkpoints_new", bsdf_root
         def sample(self, ctx, si, sample1, sample2, active=True):
             cos_theta_i = mi.Frame3f.cos_theta(si.wi)
             active &= cos_theta_i > 0
-            wo_t, pdf_t = self.sampler.sample(si.wi.torch())
+            u = None
+            if noise == "mitsuba":
+                u = torch.stack([ops.from_dlpack(sample2.x), ops.from_dlpack(sample2.y), ops.from_dlpack(sample1)], 1)
+            wo_t, pdf_t = self.sampler.sample(si.wi.torch(), u=u)
             bs = mi.BSDFSample3f()
             bs.wo = mi.Vector3f(wo_t[:, 0], wo_t[:, 1], wo_t[:, 2])
             cos_theta_o = mi.Frame3f.cos_theta(bs.wo)

@@ -94,14 +94,19 @@ int    bsdfdiff_pack_flow_tcnn(const float* tcnn_params /*host, fp32 copy of .pa
  * x0_replay: optional [n,2] externally supplied base sample (noise replay for parity); NULL = draw with
  *            Philox4x32-10, key = seed, counter = (first_index + i, offset)  -> results do not depend on
  *            how the batch is sharded across GPUs.
+ * u_noise:   optional [n,3] uniforms in [0,1) used INSTEAD of the Philox draws: the renderer's own sample stream as the
+ *            noise source (Mitsuba hands sample2.x, sample2.y, sample1 to MyBSDF.sample and the reference ignores them,
+ *            rendering/brdf_measured_disk.py:59-68).  (u0, u1) feed the Box-Muller pair of the base Gaussian; the von
+ *            Mises rejection rounds of the spherical base draw from Philox keyed by the bits of (u0, u1, u2), so the
+ *            sample is a pure function of the three uniforms.  Mutually exclusive with x0_replay.
  * out_dir:   [n,2] (EPI_RAW: x_T) or [n,3] (plugin: wo);  out_pdf: [n];  out_x0: optional [n,2].
  * T >= 1; T == 0 together with flow_packed == NULL evaluates the base distribution alone
  * (D_base.sample / D_base.log_prob, rendering/utils/model.py:387-398, 299-317). */
 int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
                     const float* wi, const void* flow_packed, int hidden, int n_hidden,
-                    const float* base_params, const float* x0_replay, uint64_t seed, uint64_t offset, int64_t first_index,
-                    float* out_dir, float* out_pdf, float* out_x0, float fix_threshold, void* fix_scratch,
-                    void* cuda_stream);
+                    const float* base_params, const float* x0_replay, const float* u_noise, uint64_t seed, uint64_t offset,
+                    int64_t first_index, float* out_dir, float* out_pdf, float* out_x0, float fix_threshold,
+                    void* fix_scratch, void* cuda_stream);
 
 /* ---- conditioning-triggered fp32 fix-up of the PREC_TC16 path (fix_threshold, fix_scratch above and below) ----
  * pdf = p_base / prod_t det J_t: where a step determinant is close to zero (or the later steps amplify an early
@@ -120,6 +125,23 @@ size_t bsdfdiff_fixup_scratch_bytes(int64_t n);
 int bsdfdiff_pdf(int precision, int domain, int epilogue, int T, int64_t n,
                  const float* wo, const float* wi, const void* flow_packed, int hidden, int n_hidden,
                  const float* base_params, float* out_pdf, float fix_threshold, void* fix_scratch, void* cuda_stream);
+
+/* ---- planar directions: zero-copy hand-off from a renderer that keeps Vector3f as three arrays ------------------------
+ * Mitsuba / Dr.Jit store si.wi and bs.wo as three separate device arrays; the reference converts them with .torch()
+ * (an interleaving copy) on the way in and rebuilds mi.Vector3f from three strided slices on the way out
+ * (rendering/brdf_measured_disk.py:66,80, rendering/bsdf_myresult.py:65,72).  These entry points read / write the three
+ * component arrays in place (DLPack-exported Dr.Jit arrays on the Python side): wi_xyz / wo_xyz / out_xyz are HOST arrays
+ * of three DEVICE pointers to [n] floats.  Plugin epilogues only (EPI_DISK / EPI_SPHERICAL / EPI_BSDF); everything else as
+ * bsdfdiff_sample / bsdfdiff_pdf, and the results are bit-identical to the interleaved calls. */
+int bsdfdiff_sample_planar(int precision, int domain, int epilogue, int T, int64_t n, const float* const wi_xyz[3],
+                           const void* flow_packed, int hidden, int n_hidden, const float* base_params,
+                           const float* x0_replay, const float* u_noise, uint64_t seed, uint64_t offset,
+                           int64_t first_index, float* const out_xyz[3], float* out_pdf, float* out_x0,
+                           float fix_threshold, void* fix_scratch, void* cuda_stream);
+int bsdfdiff_pdf_planar(int precision, int domain, int epilogue, int T, int64_t n, const float* const wo_xyz[3],
+                        const float* const wi_xyz[3], const void* flow_packed, int hidden, int n_hidden,
+                        const float* base_params, float* out_pdf, float fix_threshold, void* fix_scratch,
+                        void* cuda_stream);
 
 /* ---- log p_base(x | wi): D_base.log_prob (rendering/utils/model.py:393-398 disk, :308-317 spherical) ---------
  * x, wi: [n,2] domain coordinates.  Returned as a LOG density (no exp/log round trip: finite where p underflows). */
@@ -164,8 +186,8 @@ int bsdfdiff_multi_plan(int64_t n, const int32_t* material_id, int n_materials, 
 int bsdfdiff_sample_multi(int precision, int domain, int epilogue, int T, int64_t n, const float* wi,
                           const void* plan, int n_materials, const void* const* flows_packed,
                           const float* const* base_params, int hidden, int n_hidden, const float* x0_replay,
-                          uint64_t seed, uint64_t offset, int64_t first_index, float* out_dir, float* out_pdf,
-                          float* out_x0, float fix_threshold, void* cuda_stream);
+                          const float* u_noise, uint64_t seed, uint64_t offset, int64_t first_index, float* out_dir,
+                          float* out_pdf, float* out_x0, float fix_threshold, void* cuda_stream);
 int bsdfdiff_pdf_multi(int precision, int domain, int epilogue, int T, int64_t n, const float* wo, const float* wi,
                        const void* plan, int n_materials, const void* const* flows_packed,
                        const float* const* base_params, int hidden, int n_hidden, float* out_pdf,

@@ -337,6 +337,100 @@ def test_base_sampler_distribution(pkg):
 
 
 @pytest.mark.parametrize("prec", PRECISIONS)
+def test_renderer_uniforms_as_noise_source(pkg, prec):
+    """u= [n,3] (Mitsuba's sample2.x, sample2.y, sample1, which the reference ignores: brdf_measured_disk.py:59-68) replaces
+    the Philox draws: the disk base sample is loc + BoxMuller(u0, u1) * scale exactly; the call equals the x0-replay call on
+    the base samples it reports; the spherical base draws theta from (u0, u1) and phi ~ vonMises from a stream keyed by the
+    bits of the three uniforms (a pure function of u: deterministic, and distributed like numpy's sampler)."""
+    from scipy import stats
+    rng = np.random.default_rng(17)
+    tol = 2e-6 if prec == "fp32" else 2e-4
+    flow, base, z, pf, pb = load(pkg, DISK_FILE)
+    n = 100_003
+    wi_np = rng.uniform(-0.6, 0.6, (n, 2)).astype(np.float32)
+    u_np = rng.random((n, 3)).astype(np.float32)
+    u_np[0, 0] = 0.0                                        # [0,1) is legal input: clamped away from log(0)
+    x, pdf, x0 = pkg.ops.sample(cu(wi_np), pf, pb, 4, u=cu(u_np), precision=prec)
+    p = O.base_forward(base, wi_np)
+    ua = np.clip(u_np[:, 0].astype(np.float64), 2.9802322e-8, 0.99999994)
+    r = np.sqrt(-2.0 * np.log(ua))
+    ang = 2.0 * np.pi * np.clip(u_np[:, 1].astype(np.float64), 2.9802322e-8, 0.99999994)
+    ref0 = np.stack([p[:, 0] + r * np.cos(ang) * np.exp(p[:, 2]), p[:, 1] + r * np.sin(ang) * np.exp(p[:, 3])], 1)
+    err = np.abs(x0.cpu().numpy() - ref0) / np.maximum(1.0, np.abs(ref0))
+    assert err.max() < 50 * tol, err.max()
+    assert np.isfinite(x0.cpu().numpy()).all()
+    xr, pr, _ = pkg.ops.sample(cu(wi_np), pf, pb, 4, x0=x0, precision=prec)
+    assert torch.equal(x, xr) and torch.equal(pdf, pr)
+    x2, pdf2, _ = pkg.ops.sample(cu(wi_np), pf, pb, 4, u=cu(u_np), precision=prec)
+    assert torch.equal(x, x2) and torch.equal(pdf, pdf2)
+    with pytest.raises(ValueError, match="either x0= .* or u="):
+        pkg.ops.sample(cu(wi_np), pf, pb, 4, u=cu(u_np), x0=x0, precision=prec)
+
+    flow, base, z, pf, pb = load(pkg, BSDF_FILE)
+    n = 200_000
+    wi_np = np.tile(np.array([[0.6, 0.9]], np.float32), (n, 1))
+    u_np = rng.random((n, 3)).astype(np.float32)
+    _, _, x0 = pkg.ops.sample(cu(wi_np), pf, pb, 8, u=cu(u_np), precision=prec)
+    _, _, x0b = pkg.ops.sample(cu(wi_np), pf, pb, 8, u=cu(u_np), precision=prec)
+    assert torch.equal(x0, x0b)
+    loc, ls, mu, kappa = (a[0] for a in O.base_params_spherical(base, wi_np[:1]))
+    x0 = x0.cpu().numpy()
+    ua = np.clip(u_np[:, 0].astype(np.float64), 2.9802322e-8, 0.99999994)
+    th_ref = loc + np.sqrt(-2.0 * np.log(ua)) * np.cos(2.0 * np.pi * u_np[:, 1].astype(np.float64)) * (np.exp(ls) + 1e-3)
+    assert np.abs(x0[:, 0] - th_ref).max() < 100 * tol
+    ref = np.random.default_rng(0).vonmises(float(mu), float(kappa), 50_000)
+    ref = (ref + np.pi) % (2 * np.pi) - np.pi
+    assert stats.ks_2samp(x0[:50_000, 1], ref).pvalue > 1e-3
+    # phi depends on the third uniform too (it keys the rejection stream)
+    u_alt = u_np.copy()
+    u_alt[:, 2] = rng.random(n).astype(np.float32)
+    _, _, x0c = pkg.ops.sample(cu(wi_np), pf, pb, 8, u=cu(u_alt), precision=prec)
+    x0c = x0c.cpu().numpy()
+    assert np.array_equal(x0c[:, 0], x0[:, 0]) and (x0c[:, 1] != x0[:, 1]).mean() > 0.9
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
+@pytest.mark.parametrize("kind,path", [("disk", DISK_FILE), ("spherical", SPH_FILE), ("bsdf", BSDF_FILE)])
+def test_planar_directions_match_interleaved(pkg, kind, path, prec):
+    """sample_planar / pdf_planar read and write three separate component arrays (a Dr.Jit Vector3f through DLPack)
+    and agree bit for bit with the interleaved [n,3] calls; the inputs may be any DLPack exporter and need not share
+    one allocation."""
+    flow, base, z, pf, pb = load(pkg, path)
+    s = pkg.plugins.NeuralBSDFSampler(kind, pf, pb, precision=prec)
+    rng = np.random.default_rng(23)
+    n = 70_001
+    w = rng.normal(size=(n, 3)).astype(np.float32)
+    if kind != "bsdf":
+        w[:, 2] = np.abs(w[:, 2]) + 0.05
+    w /= np.linalg.norm(w, axis=1, keepdims=True)
+    wi = cu(w)
+    wx, wy, wz = (wi[:, c].clone() for c in range(3))          # three separate allocations
+
+    class Exporter:                                            # speaks DLPack only, like a Dr.Jit array
+        def __init__(self, t):
+            self.t = t
+
+        def __dlpack__(self, stream=None):
+            return self.t.__dlpack__(stream=stream) if stream is not None else self.t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self.t.__dlpack_device__()
+
+    wo, pdf = s.sample(wi, seed=4, offset=12)
+    ox, oy, oz, pdf_p = s.sample_planar((Exporter(wx), wy, Exporter(wz)), seed=4, offset=12)
+    assert torch.equal(torch.stack([ox, oy, oz], 1), wo) and torch.equal(pdf_p, pdf)
+    p = s.pdf(wi, wo)
+    p_p = s.pdf_planar((wx, wy, wz), (ox, Exporter(oy), oz))
+    assert torch.equal(p, p_p)
+    u = cu(rng.random((n, 3)).astype(np.float32))
+    a = s.sample(wi, u=u)
+    b = s.sample_planar((wx, wy, wz), u=u)
+    assert torch.equal(torch.stack(b[:3], 1), a[0]) and torch.equal(b[3], a[1])
+    with pytest.raises(ValueError, match="components must be contiguous"):
+        s.sample_planar((wi[:, 0], wi[:, 1], wi[:, 2]), seed=1)         # strided views are not planar arrays
+
+
+@pytest.mark.parametrize("prec", PRECISIONS)
 def test_chi_square_two_sample_vs_oracle(pkg, prec):
     """64K outgoing samples for one fixed wi (BASELINE config 1): histogram of the kernel's own Philox
     samples vs the oracle pushed through INDEPENDENT base samples -> two-sample chi-square."""
@@ -652,7 +746,7 @@ def test_tmem_aliasing_build_is_bit_identical(pkg):
         out_x = torch.empty(n, 2, device="cuda")
         out_p = torch.empty(n, device="cuda")
         rc = alt.bsdfdiff_sample(L.PREC_TC16, pf.domain, 0, T, n, wi.data_ptr(), pf.blob.data_ptr(), pf.hidden,
-                                 pf.n_hidden, pb.data_ptr(), x0.data_ptr(), 0, 0, 0, out_x.data_ptr(), out_p.data_ptr(),
+                                 pf.n_hidden, pb.data_ptr(), x0.data_ptr(), None, 0, 0, 0, out_x.data_ptr(), out_p.data_ptr(),
                                  None, 0.0, None, torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         torch.cuda.synchronize()

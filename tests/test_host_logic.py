@@ -95,14 +95,15 @@ def test_argument_validation_without_gpu(built_lib):
     with pytest.raises(L.BsdfDiffError):
         built_lib.weights.pack_base_arrays(np.zeros((16, 14)), np.zeros(16), np.zeros((4, 16)), np.zeros(3), "cpu")
     # invalid arguments are rejected before any CUDA call
-    assert L.lib.bsdfdiff_sample(0, 0, 0, 4, 16, None, None, 32, 3, None, None, 0, 0, 0, None, None, None, 0.0, None,
+    assert L.lib.bsdfdiff_sample(0, 0, 0, 4, 16, None, None, 32, 3, None, None, None, 0, 0, 0, None, None, None, 0.0, None,
                                  None) == -1
-    assert L.lib.bsdfdiff_sample(0, 0, 2, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, None, 0.0, None,
+    assert L.lib.bsdfdiff_sample(0, 0, 2, 4, 16, 1, 1, 32, 3, 1, None, None, 0, 0, 0, 1, 1, None, 0.0, None,
                                  None) == -1                          # spherical epilogue on a disk net
     assert L.lib.bsdfdiff_pdf(0, 1, 0, -1, 16, 1, 1, 1, 32, 4, 1, 1, 0.0, None, None) == -1
     # the fix-up needs its scratch buffer, and (sample) a base sample to replay
-    assert L.lib.bsdfdiff_sample(1, 0, 0, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, 1, 0.25, None, None) == -1
-    assert L.lib.bsdfdiff_sample(1, 0, 0, 4, 16, 1, 1, 32, 3, 1, None, 0, 0, 0, 1, 1, None, 0.25, 1, None) == -1
+    assert L.lib.bsdfdiff_sample(1, 0, 0, 4, 16, 1, 1, 32, 3, 1, None, None, 0, 0, 0, 1, 1, 1, 0.25, None, None) == -1
+    assert L.lib.bsdfdiff_sample(1, 0, 0, 4, 16, 1, 1, 32, 3, 1, None, None, 0, 0, 0, 1, 1, None, 0.25, 1, None) == -1
+    assert L.lib.bsdfdiff_sample(0, 0, 0, 4, 16, 1, 1, 32, 3, 1, 1, 1, 0, 0, 0, 1, 1, None, 0.0, None, None) == -1   # x0 AND u_noise
     assert L.lib.bsdfdiff_base_log_prob(2, 16, 1, 1, 1, 1, None) == -1
     assert L.lib.bsdfdiff_fixup_scratch_bytes(1000) == 16 + 4000
     assert L.lib.bsdfdiff_error_string(1).decode().startswith("ok (")
