@@ -3,6 +3,7 @@
 #include "../../include/bsdfdiff.h"
 #include "common.cuh"
 #include "multi.cuh"
+#include "train.cuh"
 
 #include <cstring>
 #include <vector>
@@ -465,4 +466,31 @@ extern "C" int bsdfdiff_pdf_planar(int precision, int domain, int epilogue, int 
     int rc = fill_shape(P, flow_packed, domain, hidden, n_hidden);
     if (rc) return rc;
     return dispatch_fixup(precision, P, static_cast<cudaStream_t>(cuda_stream), fix_threshold, fix_scratch);
+}
+
+// ------------------------------------------------------------------------------------------------
+// training step (train.cu)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t bsdfdiff_flow_param_count(int in_dim, int hidden, int n_hidden) {
+    if (in_dim < 1 || in_dim > 32 || (hidden != 32 && hidden != 64) || n_hidden < 1 || n_hidden > 8) return 0;
+    return (size_t)f32_image_floats(in_dim, hidden, n_hidden);
+}
+
+extern "C" int bsdfdiff_flow_matching_step(int domain, int hidden, int n_hidden, int64_t n, const float* x0, const float* x1,
+                                           const float* wi, const float* alpha, float* weights, float* grad, float* adam_m,
+                                           float* adam_v, float lr, float beta1, float beta2, float eps, int64_t step,
+                                           int apply_update, float* loss_out, void* sync_scratch, void* cuda_stream) {
+    if ((domain != kDisk && domain != kSpherical) || n < 1 || !x0 || !x1 || !wi || !weights || !grad || !loss_out ||
+        !sync_scratch || (apply_update && (!adam_m || !adam_v || step < 1)))
+        return BSDFDIFF_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    TrainParams P{};
+    P.domain = domain; P.in_dim = (domain == kDisk) ? 25 : 26; P.hidden = hidden; P.n_hidden = n_hidden; P.n = n;
+    P.x0 = x0; P.x1 = x1; P.wi = wi; P.alpha = alpha; P.weights = weights; P.grad = grad; P.adam_m = adam_m; P.adam_v = adam_v;
+    P.lr = lr; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps; P.step = step; P.apply_update = apply_update;
+    P.loss = loss_out; P.ticket = static_cast<unsigned int*>(sync_scratch);
+    if (cudaMemsetAsync(loss_out, 0, sizeof(float), stream) != cudaSuccess) return fail_cuda();
+    const int rc = launch_flow_matching_step(P, stream);
+    if (rc == -3) return fail_cuda();
+    return rc;
 }

@@ -193,6 +193,25 @@ int bsdfdiff_pdf_multi(int precision, int domain, int epilogue, int T, int64_t n
                        const float* const* base_params, int hidden, int n_hidden, float* out_pdf,
                        float fix_threshold, void* cuda_stream);
 
+/* ---- training step of the flow nets: fused forward + backward + Adam ----------------------------------
+ * Replaces one iteration of the reference's diffusion_stage / rectify_stage loops
+ * (learning_repo_cleanup/disk_domain_sampling.py:49-58,123-131; spherical_domain_sampling.py:55-76; the
+ * kernel_mlp_fused_backward analogue, tiny-cuda-nn/src/fully_fused_mlp.cu:150-259):
+ *     alpha = linspace(0,1,n) (or the given column);  x_alpha = (1 - alpha) x0 + alpha x1  (spherical: x1.phi first moved
+ *     to within pi of x0.phi, net input (theta, sin phi, cos phi));  pred = D(x_alpha, alpha, wi);
+ *     loss = mean((pred - (x1 - x0))^2);  grad = dloss/dW;  torch.optim.Adam update (amsgrad off, no weight decay).
+ * weights / grad / adam_m / adam_v: device fp32 vectors of bsdfdiff_flow_param_count() elements in the checkpoint layout
+ * (linear1.weight [H,in] row-major, linear2.., output.weight [2,H], concatenated): these ARE the master weights.
+ * grad must be zero on entry; with apply_update != 0 it is zero again on exit and the weights / moments are updated
+ * (step = 1-based step count for the bias correction), with apply_update == 0 it holds dloss/dW (weights untouched).
+ * loss_out: device float (the step's loss).  sync_scratch: 4 zero bytes of device memory (left zero).  One launch, no host
+ * synchronisation, CUDA-graph capturable.  fp32 arithmetic; hidden 32 (3 or 4 hidden layers) or 64 (up to 6). */
+size_t bsdfdiff_flow_param_count(int in_dim, int hidden, int n_hidden);
+int bsdfdiff_flow_matching_step(int domain, int hidden, int n_hidden, int64_t n, const float* x0, const float* x1,
+                                const float* wi, const float* alpha, float* weights, float* grad, float* adam_m,
+                                float* adam_v, float lr, float beta1, float beta2, float eps, int64_t step,
+                                int apply_update, float* loss_out, void* sync_scratch, void* cuda_stream);
+
 /* ---- measured-BSDF ground truth: Mitsuba 3 `measured` eval of an RGL tensor file, and the plugins' weight + firefly clamp ----
  * Replaces  self.bsdf.eval(ctx, si, bs.wo)  (mi.load_dict({"type": "measured", ...}), rendering/brdf_measured_disk.py:36-42,92
  * and rendering/brdf_measured_spherical.py:45-51,100) and the Dr.Jit<->torch round trips of the firefly clamp
