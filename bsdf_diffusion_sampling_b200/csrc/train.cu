@@ -35,45 +35,75 @@ __device__ __forceinline__ void silu_both(float z, float& h, float& g) {
 
 template <int H, int ROWS>
 struct TrainSmem {
-    // per-thread columns, element e of row r at col[e * ROWS + r]
+    // per-thread columns, element e of row r at col[e * RS + r].  RS = ROWS + 4: with RS = ROWS every column would start
+    // in bank 0 and the float4 reads of the weight-gradient product (different columns, same rows) would be 8-way
+    // bank conflicts; + 4 floats shifts consecutive columns by one float4
+    static constexpr int RS = ROWS + 4;
     static constexpr int kIn = 28;                       // first-layer input (25 | 26), padded
     __host__ __device__ static size_t floats(int in_dim, int n_hidden) {
         const size_t w = (size_t)in_dim * H + (size_t)(n_hidden - 1) * H * H + 2 * H;
-        return ((w + 3) & ~(size_t)3) + (size_t)ROWS * ((size_t)n_hidden * H + kIn + 2 * H);
+        return ((w + 3) & ~(size_t)3) + (size_t)RS * ((size_t)n_hidden * H + kIn + 2 * H);
     }
 };
 
-// dW[j][k] (+)= sum_r D[j][r] * P[k][r] over the tile; outputs (j, k) are dealt to the CTA's threads in blocks of 4 k's.
-// D: [J][ROWS], P: [K][ROWS] (shared-memory columns); grad row-major [J][K] (torch layout)
-template <int ROWS>
-__device__ __forceinline__ void tile_outer(const float* __restrict__ D, int J, const float* __restrict__ P, int K,
-                                           float* __restrict__ grad) {
-    const int kb = (K + 3) >> 2;                         // blocks of 4 consecutive k
-    for (int o = threadIdx.x; o < J * kb; o += ROWS) {
-        const int j = o / kb, k0 = (o - j * kb) << 2;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        const float4* d4 = reinterpret_cast<const float4*>(D + (size_t)j * ROWS);
-        const float4* p0 = reinterpret_cast<const float4*>(P + (size_t)k0 * ROWS);
-        const float4* p1 = reinterpret_cast<const float4*>(P + (size_t)min(k0 + 1, K - 1) * ROWS);
-        const float4* p2 = reinterpret_cast<const float4*>(P + (size_t)min(k0 + 2, K - 1) * ROWS);
-        const float4* p3 = reinterpret_cast<const float4*>(P + (size_t)min(k0 + 3, K - 1) * ROWS);
+// acc[b] (+)= sum_r D[j][r] * P[k0 + b][r] over the tile, for the (j, block of 4 consecutive k) pairs dealt to this thread:
+// pair o = threadIdx.x + s * ROWS, s < SLOTS.  D: [J][RS], P: [K][RS] (shared-memory columns).  The sums stay in
+// registers across all tiles of the CTA and reach the global gradient once, at the end (flush_outer).
+// Work item o of a layer's weight-gradient product: output row j = o / kb and the four columns k = kq + b * kb
+// (kq = o % kb, kb = ceil(K / 4), b = 0..3).  Strided columns: the threads of a warp then read CONSECUTIVE columns of P,
+// which the RS = ROWS + 4 padding spreads over all banks (blocks of 4 adjacent columns would be 4-way conflicts).
+template <int ROWS, int RS>
+__device__ __forceinline__ void tile_outer_one(const float* __restrict__ D, const float* __restrict__ P, int K, int o,
+                                               float* acc) {
+    const int kb = (K + 3) >> 2;
+    const int j = o / kb, kq = o - j * kb;
+    float a0 = acc[0], a1 = acc[1], a2 = acc[2], a3 = acc[3];
+    const float4* d4 = reinterpret_cast<const float4*>(D + (size_t)j * RS);
+    const float4* p0 = reinterpret_cast<const float4*>(P + (size_t)kq * RS);
+    const float4* p1 = reinterpret_cast<const float4*>(P + (size_t)min(kq + kb, K - 1) * RS);
+    const float4* p2 = reinterpret_cast<const float4*>(P + (size_t)min(kq + 2 * kb, K - 1) * RS);
+    const float4* p3 = reinterpret_cast<const float4*>(P + (size_t)min(kq + 3 * kb, K - 1) * RS);
 #pragma unroll 4
-        for (int r = 0; r < ROWS / 4; ++r) {
-            const float4 d = d4[r];
-            float4 p = p0[r];
-            a0 = fmaf(d.x, p.x, a0); a0 = fmaf(d.y, p.y, a0); a0 = fmaf(d.z, p.z, a0); a0 = fmaf(d.w, p.w, a0);
-            p = p1[r];
-            a1 = fmaf(d.x, p.x, a1); a1 = fmaf(d.y, p.y, a1); a1 = fmaf(d.z, p.z, a1); a1 = fmaf(d.w, p.w, a1);
-            p = p2[r];
-            a2 = fmaf(d.x, p.x, a2); a2 = fmaf(d.y, p.y, a2); a2 = fmaf(d.z, p.z, a2); a2 = fmaf(d.w, p.w, a2);
-            p = p3[r];
-            a3 = fmaf(d.x, p.x, a3); a3 = fmaf(d.y, p.y, a3); a3 = fmaf(d.z, p.z, a3); a3 = fmaf(d.w, p.w, a3);
-        }
-        float* g = grad + (size_t)j * K + k0;
-        atomicAdd(g, a0);
-        if (k0 + 1 < K) atomicAdd(g + 1, a1);
-        if (k0 + 2 < K) atomicAdd(g + 2, a2);
-        if (k0 + 3 < K) atomicAdd(g + 3, a3);
+    for (int r = 0; r < ROWS / 4; ++r) {
+        const float4 d = d4[r];
+        float4 p = p0[r];
+        a0 = fmaf(d.x, p.x, a0); a0 = fmaf(d.y, p.y, a0); a0 = fmaf(d.z, p.z, a0); a0 = fmaf(d.w, p.w, a0);
+        p = p1[r];
+        a1 = fmaf(d.x, p.x, a1); a1 = fmaf(d.y, p.y, a1); a1 = fmaf(d.z, p.z, a1); a1 = fmaf(d.w, p.w, a1);
+        p = p2[r];
+        a2 = fmaf(d.x, p.x, a2); a2 = fmaf(d.y, p.y, a2); a2 = fmaf(d.z, p.z, a2); a2 = fmaf(d.w, p.w, a2);
+        p = p3[r];
+        a3 = fmaf(d.x, p.x, a3); a3 = fmaf(d.y, p.y, a3); a3 = fmaf(d.z, p.z, a3); a3 = fmaf(d.w, p.w, a3);
+    }
+    acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3;
+}
+// acc[0..3] of work item o -> the global gradient (row-major [J][K], torch layout)
+__device__ __forceinline__ void add_outer_one(int K, int o, const float* acc, float* __restrict__ grad) {
+    const int kb = (K + 3) >> 2;
+    const int j = o / kb, kq = o - j * kb;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+        if (kq + b * kb < K) atomicAdd(grad + (size_t)j * K + kq + b * kb, acc[b]);
+}
+template <int ROWS, int RS, int SLOTS>
+__device__ __forceinline__ void tile_outer(const float* __restrict__ D, int J, const float* __restrict__ P, int K,
+                                           float (*acc)[4]) {
+    const int kb = (K + 3) >> 2;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+        const int o = threadIdx.x + sl * ROWS;
+        if (o >= J * kb) break;
+        tile_outer_one<ROWS, RS>(D, P, K, o, acc[sl]);
+    }
+}
+template <int ROWS, int SLOTS>
+__device__ __forceinline__ void flush_outer(int J, int K, const float (*acc)[4], float* __restrict__ grad) {
+    const int kb = (K + 3) >> 2;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {
+        const int o = threadIdx.x + sl * ROWS;
+        if (o >= J * kb) break;
+        add_outer_one(K, o, acc[sl], grad);
     }
 }
 
@@ -82,13 +112,25 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
     extern __shared__ __align__(16) float smem[];
     const int in_dim = P.in_dim, L = P.n_hidden;
     const int n_w = in_dim * H + (L - 1) * H * H + 2 * H;
+    constexpr int RS = TrainSmem<H, ROWS>::RS;
+    constexpr int SLOTS = (H * (H / 4) + ROWS - 1) / ROWS;       // (j, 4-k block) pairs of one layer's gradient per thread
+    // H = 32: the gradient sums of up to 4 hidden layers stay in registers for the CTA's lifetime (28 accumulators per
+    // thread); H = 64 would need 384, so there every tile adds its product to the global gradient directly
+    constexpr bool kRegAcc = (H == 32);
+    constexpr int kMaxL = kRegAcc ? 4 : 1;
     float* Wt = smem;                                    // transposed image: W1t [in][H], W2t.. [H][H], Woutt [H][2]
     float* col = smem + ((n_w + 3) & ~3);
-    float* Z = col;                                      // [L][H][ROWS]
-    float* IN = Z + (size_t)L * H * ROWS;                // [kIn][ROWS]
-    float* D = IN + (size_t)TrainSmem<H, ROWS>::kIn * ROWS;   // [H][ROWS]  delta_z of the current layer
-    float* HP = D + (size_t)H * ROWS;                    // [H][ROWS]  input of the current layer (h_{l-1})
+    float* Z = col;                                      // [L][H][RS]
+    float* IN = Z + (size_t)L * H * RS;                  // [kIn][RS]
+    float* D = IN + (size_t)TrainSmem<H, ROWS>::kIn * RS;   // [H][RS]  delta_z of the current layer
+    float* HP = D + (size_t)H * RS;                      // [H][RS]  input of the current layer (h_{l-1})
     const int tid = threadIdx.x;
+    float gacc[kMaxL][SLOTS][4], gout[1][4];             // this thread's share of dW_1..dW_L and dWout, summed over the CTA's tiles
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l)
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) gacc[l][sl][0] = gacc[l][sl][1] = gacc[l][sl][2] = gacc[l][sl][3] = 0.0f;
+    gout[0][0] = gout[0][1] = gout[0][2] = gout[0][3] = 0.0f;
 
     {   // stage the weights, transposed (torch layout [out][in] -> [in][out])
         const float* w = P.weights;
@@ -119,9 +161,9 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
         float t0 = b.x - a.x, t1 = b.y - a.y;            // regression target omega_o - x_0
         int k0;
         if (P.domain == kDisk) {
-            IN[0 * ROWS + tid] = (1.0f - alpha) * a.x + alpha * b.x;
-            IN[1 * ROWS + tid] = (1.0f - alpha) * a.y + alpha * b.y;
-            IN[2 * ROWS + tid] = alpha;
+            IN[0 * RS + tid] = (1.0f - alpha) * a.x + alpha * b.x;
+            IN[1 * RS + tid] = (1.0f - alpha) * a.y + alpha * b.y;
+            IN[2 * RS + tid] = alpha;
             k0 = 3;
         } else {
             // spherical_domain_sampling.py:61-72: move omega_o.phi to within pi of x_0.phi, interpolate, embed periodically
@@ -130,14 +172,14 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
             const float th = (1.0f - alpha) * a.x + alpha * b.x, ph = (1.0f - alpha) * a.y + alpha * b.y;
             float s, c;
             sincosf(ph, &s, &c);
-            IN[0 * ROWS + tid] = th; IN[1 * ROWS + tid] = s; IN[2 * ROWS + tid] = c; IN[3 * ROWS + tid] = alpha;
+            IN[0 * RS + tid] = th; IN[1 * RS + tid] = s; IN[2 * RS + tid] = c; IN[3 * RS + tid] = alpha;
             k0 = 4;
         }
         {
             float e[kPE5];
             positional_encoding<5>(wi.x, wi.y, e);
 #pragma unroll
-            for (int k = 0; k < kPE5; ++k) IN[(k0 + k) * ROWS + tid] = e[k];
+            for (int k = 0; k < kPE5; ++k) IN[(k0 + k) * RS + tid] = e[k];
         }
 
         // ---- forward ---------------------------------------------------------------------------------------
@@ -147,11 +189,11 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
             float az[H];
 #pragma unroll
             for (int j = 0; j < H; ++j) az[j] = 0.0f;
-            const float* zin = Z + (size_t)(l - 1) * H * ROWS;
+            const float* zin = Z + (size_t)(l - 1) * H * RS;
             for (int k = 0; k < K; ++k) {
                 float hk;
-                if (l == 0) hk = IN[k * ROWS + tid];
-                else { const float z = zin[k * ROWS + tid]; hk = z / (1.0f + expf(-z)); }
+                if (l == 0) hk = IN[k * RS + tid];
+                else { const float z = zin[k * RS + tid]; hk = z / (1.0f + expf(-z)); }
                 const float4* w4 = reinterpret_cast<const float4*>(Wl + k * H);
 #pragma unroll
                 for (int j4 = 0; j4 < H / 4; ++j4) {
@@ -162,19 +204,19 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
                     az[4 * j4 + 3] = fmaf(hk, w.w, az[4 * j4 + 3]);
                 }
             }
-            float* zo = Z + (size_t)l * H * ROWS;
+            float* zo = Z + (size_t)l * H * RS;
 #pragma unroll
-            for (int j = 0; j < H; ++j) zo[j * ROWS + tid] = az[j];
+            for (int j = 0; j < H; ++j) zo[j * RS + tid] = az[j];
             Wl += K * H;
         }
         // output layer + loss; HP <- h_L, D rows 0..1 <- delta_out
         float p0 = 0.0f, p1 = 0.0f;
         {
-            const float* zl = Z + (size_t)(L - 1) * H * ROWS;
+            const float* zl = Z + (size_t)(L - 1) * H * RS;
             for (int k = 0; k < H; ++k) {
-                const float z = zl[k * ROWS + tid];
+                const float z = zl[k * RS + tid];
                 const float h = z / (1.0f + expf(-z));
-                HP[k * ROWS + tid] = h;
+                HP[k * RS + tid] = h;
                 const float2 w = reinterpret_cast<const float2*>(Wl)[k];
                 p0 = fmaf(h, w.x, p0); p1 = fmaf(h, w.y, p1);
             }
@@ -182,21 +224,20 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
         float d0 = valid ? (p0 - t0) : 0.0f, d1 = valid ? (p1 - t1) : 0.0f;
         loss_acc += 0.5f * (d0 * d0 + d1 * d1);
         d0 *= inv_n; d1 *= inv_n;
-        D[0 * ROWS + tid] = d0; D[1 * ROWS + tid] = d1;
+        D[0 * RS + tid] = d0; D[1 * RS + tid] = d1;
         __syncthreads();
 
         // ---- backward ----------------------------------------------------------------------------------------
-        const int off_out = in_dim * H + (L - 1) * H * H;
-        tile_outer<ROWS>(D, 2, HP, H, P.grad + off_out);                  // dWout [2][H]
+        tile_outer<ROWS, RS, 1>(D, 2, HP, H, gout);                       // dWout [2][H]
         // delta_z of the last hidden layer
         float dz[H];
         {
-            const float* zl = Z + (size_t)(L - 1) * H * ROWS;
+            const float* zl = Z + (size_t)(L - 1) * H * RS;
 #pragma unroll
             for (int k = 0; k < H; ++k) {
                 const float2 w = reinterpret_cast<const float2*>(Wl)[k];
                 float h, g;
-                silu_both(zl[k * ROWS + tid], h, g);
+                silu_both(zl[k * RS + tid], h, g);
                 dz[k] = (d0 * w.x + d1 * w.y) * g;
             }
         }
@@ -205,13 +246,27 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
             const int off = (l == 0) ? 0 : in_dim * H + (l - 1) * H * H;
             __syncthreads();                              // everyone is done reading D / HP of the layer above
 #pragma unroll
-            for (int j = 0; j < H; ++j) D[j * ROWS + tid] = dz[j];
-            const float* src = (l == 0) ? IN : Z + (size_t)(l - 1) * H * ROWS;
+            for (int j = 0; j < H; ++j) D[j * RS + tid] = dz[j];
+            const float* src = (l == 0) ? IN : Z + (size_t)(l - 1) * H * RS;
             if (l > 0) {
-                for (int k = 0; k < H; ++k) { const float z = src[k * ROWS + tid]; HP[k * ROWS + tid] = z / (1.0f + expf(-z)); }
+                for (int k = 0; k < H; ++k) { const float z = src[k * RS + tid]; HP[k * RS + tid] = z / (1.0f + expf(-z)); }
             }
             __syncthreads();
-            tile_outer<ROWS>(D, H, (l == 0) ? IN : HP, K, P.grad + off);   // dW_l [H][K]
+            // dW_l [H][K]
+            if (kRegAcc) {                                // the layer index selects the register block at compile time
+#pragma unroll
+                for (int q = 0; q < kMaxL; ++q)
+                    if (q == l) tile_outer<ROWS, RS, SLOTS>(D, H, (l == 0) ? IN : HP, K, gacc[q]);
+            } else {
+#pragma unroll 1
+                for (int sl0 = 0; sl0 < SLOTS; ++sl0) {   // one slot at a time through a 4-float scratch block
+                    float t4[1][4] = {{0.0f, 0.0f, 0.0f, 0.0f}};
+                    const int o = tid + sl0 * ROWS, kb = (K + 3) >> 2;
+                    if (o >= H * kb) break;
+                    tile_outer_one<ROWS, RS>(D, (l == 0) ? IN : HP, K, o, t4[0]);
+                    add_outer_one(K, o, t4[0], P.grad + off);
+                }
+            }
             if (l > 0) {
                 // delta_h_{l-1}[k] = sum_j W_l[j][k] delta_z_l[j] = sum_j Wt_l[k][j] dz[j];  delta_z_{l-1} = delta_h * silu'(z_{l-1})
                 const float* Wc = Wt + off;
@@ -227,7 +282,7 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
                         acc = fmaf(w.z, dz[4 * j4 + 2], acc); acc = fmaf(w.w, dz[4 * j4 + 3], acc);
                     }
                     float h, g;
-                    silu_both(src[k * ROWS + tid], h, g);
+                    silu_both(src[k * RS + tid], h, g);
                     nz[k] = acc * g;
                 }
 #pragma unroll
@@ -236,6 +291,14 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
         }
         __syncthreads();                                  // the next tile overwrites IN / Z / D / HP
     }
+
+    // ---- this CTA's gradient sums -> global gradient (one atomic per weight per CTA) ---------------------------------
+    if (kRegAcc) {
+#pragma unroll
+        for (int q = 0; q < kMaxL; ++q)
+            if (q < L) flush_outer<ROWS, SLOTS>(H, (q == 0) ? in_dim : H, gacc[q], P.grad + ((q == 0) ? 0 : in_dim * H + (q - 1) * H * H));
+    }
+    flush_outer<ROWS, 1>(2, H, gout, P.grad + in_dim * H + (L - 1) * H * H);
 
     // ---- loss, then Adam by the last CTA -------------------------------------------------------------------------
 #pragma unroll
@@ -282,9 +345,11 @@ static int launch_train_t(const TrainParams& P, cudaStream_t stream) {
 }
 
 int launch_flow_matching_step(const TrainParams& P, cudaStream_t stream) {
-    if (P.n_hidden < 1 || P.n_hidden > 8) return -2;
-    if (P.hidden == 32) return launch_train_t<32, 128>(P, stream);
-    if (P.hidden == 64) return launch_train_t<64, 64>(P, stream);     // 64-row tiles: the z columns of 6 layers + 89 KB of weights fill the SM
+    if (P.n_hidden < 1) return -2;
+    if (P.hidden == 32) return P.n_hidden <= 4 ? launch_train_t<32, 128>(P, stream) : -2;
+    if (P.hidden == 64 && P.n_hidden > 6) return -2;
+    // 64-wide nets: the z columns of 6 layers + 89 KB of weights only fit with 32-row tiles
+    if (P.hidden == 64) return P.n_hidden <= 4 ? launch_train_t<64, 64>(P, stream) : launch_train_t<64, 32>(P, stream);
     return -2;
 }
 
