@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbsdfdiff.so")
-SOURCES = ["capi.cu", "flow_simt.cu", "flow_tc.cu", "measured.cu", "multi.cu", "train.cu"]
+SOURCES = ["capi.cu", "flow_simt.cu", "flow_tc.cu", "measured.cu", "multi.cu", "train.cu", "flow_lane8.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 # per-source extras.  The tensor-core path works at fp16-operand accuracy, so its fp32 prologue/epilogue math (base

@@ -191,9 +191,16 @@ extern "C" int bsdfdiff_pack_flow_tcnn(const float* p, int in_dim, int out_dim, 
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
+// fp32 CUDA-core launch: eight lanes per query for the 32-wide sampler nets (flow_lane8.cu), one thread per query for
+// everything else (64-wide nets, forward-only mode, T == 0: flow_simt.cu)
+static int launch_fp32(const FlowParams& P, cudaStream_t stream) {
+    const int rc = launch_lane8(P, stream);
+    return rc == -2 ? launch_simt(P, stream) : rc;
+}
+
 static int dispatch(int precision, const FlowParams& P, cudaStream_t stream) {
     int rc;
-    if (precision == BSDFDIFF_PREC_FP32 || P.T == 0) rc = launch_simt(P, stream);
+    if (precision == BSDFDIFF_PREC_FP32 || P.T == 0) rc = launch_fp32(P, stream);
     else if (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP) {
         rc = launch_tc(P, stream, precision);
         // shapes the tcgen05 kernel does not cover (more than 6 hidden layers; sample/pdf with a 64-wide net -- none of
@@ -202,7 +209,7 @@ static int dispatch(int precision, const FlowParams& P, cudaStream_t stream) {
         if (rc == -2) {
             FlowParams Q = P;
             Q.fix_thr = 0.0f; Q.fix_count = nullptr; Q.fix_list = nullptr;
-            rc = launch_simt(Q, stream);
+            rc = launch_fp32(Q, stream);
             if (rc == 0) return BSDFDIFF_OK_FP32_REROUTE;
         }
     }
@@ -228,7 +235,7 @@ static int dispatch_fixup(int precision, FlowParams P, cudaStream_t stream, floa
     FlowParams Q = P;
     Q.fix_pass = 1;
     if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; Q.u_noise = nullptr; }
-    rc = launch_simt(Q, stream);
+    rc = launch_fp32(Q, stream);
     if (rc == -3) return fail_cuda();
     return rc;
 }
@@ -364,18 +371,18 @@ static int dispatch_multi(int precision, FlowParams P, int n_materials, const vo
         if (P.mode == kModeSample && !P.x0 && !P.out_x0) P.out_x0 = v.x0;     // the fix-up pass replays the base sample
         if (cudaMemsetAsync(v.fix_count, 0, sizeof(unsigned int) * 256, stream) != cudaSuccess) return fail_cuda();
     }
-    int rc = tc ? launch_tc(P, stream, precision) : launch_simt(P, stream);
+    int rc = tc ? launch_tc(P, stream, precision) : launch_fp32(P, stream);
     int note = BSDFDIFF_OK;
     if (tc && rc == -2) {                       // shape outside the tensor-core kernel: the fp32 kernel walks the same plan
         FlowParams Q = P;
         Q.fix_thr = 0.0f; Q.fix_count = nullptr; Q.fix_list = nullptr;
-        rc = launch_simt(Q, stream);
+        rc = launch_fp32(Q, stream);
         note = BSDFDIFF_OK_FP32_REROUTE;
     } else if (fix && rc == 0) {
         FlowParams Q = P;
         Q.fix_pass = 1;
         if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; Q.u_noise = nullptr; }
-        rc = launch_simt(Q, stream);
+        rc = launch_fp32(Q, stream);
     }
     if (rc == -3) return fail_cuda();
     if (rc == -4) return BSDFDIFF_ENOTSM100;

@@ -384,6 +384,7 @@ __device__ __forceinline__ void store_pdf(const FlowParams& P, long long i, floa
 }
 
 int launch_simt(const FlowParams& P, cudaStream_t stream);
+int launch_lane8(const FlowParams& P, cudaStream_t stream);      // eight lanes per query: 32-wide sampler nets, sample / pdf, T >= 1
 int launch_tc(const FlowParams& P, cudaStream_t stream, int variant);
 unsigned int tc_timeout_flag();
 int tc_trace_read(unsigned long long* out, int max_words);

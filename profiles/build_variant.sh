@@ -7,7 +7,7 @@ name=$1; shift
 cd "$(dirname "$0")/.."
 mkdir -p variants/obj_$name
 C=bsdf_diffusion_sampling_b200/csrc
-for f in capi flow_simt flow_tc measured multi train; do
+for f in capi flow_simt flow_tc measured multi train flow_lane8; do
   extra=""
   if [ $f = flow_tc ]; then extra="-ftz=true -prec-div=false -prec-sqrt=false"; fi
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC \
