@@ -28,7 +28,7 @@ EXPORTS = [
     "bsdfdiff_measured_blob_bytes", "bsdfdiff_measured_pack", "bsdfdiff_measured_eval", "bsdfdiff_measured_weight",
     "bsdfdiff_multi_scratch_bytes", "bsdfdiff_multi_plan", "bsdfdiff_sample_multi", "bsdfdiff_pdf_multi",
     "bsdfdiff_sample_planar", "bsdfdiff_pdf_planar",
-    "bsdfdiff_flow_param_count", "bsdfdiff_flow_matching_step",
+    "bsdfdiff_flow_param_count", "bsdfdiff_flow_matching_step", "bsdfdiff_base_nll_step",
 ]
 
 _c = ctypes
@@ -77,6 +77,8 @@ def _load() -> ctypes.CDLL:
     lib.bsdfdiff_flow_matching_step.restype = _i
     lib.bsdfdiff_flow_matching_step.argtypes = [_i, _i, _i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f,
                                                 _i64, _i, _vp, _vp, _vp]
+    lib.bsdfdiff_base_nll_step.restype = _i
+    lib.bsdfdiff_base_nll_step.argtypes = [_i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _f, _f, _f, _f, _i64, _i, _vp, _vp, _vp]
     _p3 = _c.POINTER(_vp)
     lib.bsdfdiff_sample_planar.argtypes = [_i, _i, _i, _i, _i64, _p3, _vp, _i, _i, _vp, _vp, _vp, _u64, _u64, _i64,
                                            _p3, _vp, _vp, _f, _vp, _vp]

@@ -501,3 +501,20 @@ extern "C" int bsdfdiff_flow_matching_step(int domain, int hidden, int n_hidden,
     if (rc == -3) return fail_cuda();
     return rc;
 }
+
+extern "C" int bsdfdiff_base_nll_step(int domain, int64_t n, const float* x, const float* wi, float* base_params, float* grad,
+                                      float* adam_m, float* adam_v, float lr, float beta1, float beta2, float eps,
+                                      int64_t step, int apply_update, float* loss_out, void* sync_scratch, void* cuda_stream) {
+    if ((domain != kDisk && domain != kSpherical) || n < 1 || !x || !wi || !base_params || !grad || !loss_out ||
+        !sync_scratch || (apply_update && (!adam_m || !adam_v || step < 1)))
+        return BSDFDIFF_EINVAL;
+    cudaStream_t stream = static_cast<cudaStream_t>(cuda_stream);
+    TrainParams P{};
+    P.domain = domain; P.n = n; P.x1 = x; P.wi = wi; P.weights = base_params; P.grad = grad; P.adam_m = adam_m; P.adam_v = adam_v;
+    P.lr = lr; P.beta1 = beta1; P.beta2 = beta2; P.eps = eps; P.step = step; P.apply_update = apply_update;
+    P.loss = loss_out; P.ticket = static_cast<unsigned int*>(sync_scratch);
+    if (cudaMemsetAsync(loss_out, 0, sizeof(float), stream) != cudaSuccess) return fail_cuda();
+    const int rc = launch_base_nll_step(P, stream);
+    if (rc == -3) return fail_cuda();
+    return rc;
+}

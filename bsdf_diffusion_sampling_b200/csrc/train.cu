@@ -107,6 +107,36 @@ __device__ __forceinline__ void flush_outer(int J, int K, const float (*acc)[4],
     }
 }
 
+// Loss accumulation + torch.optim.Adam by the last CTA to finish (device-side ticket): shared by both training kernels.
+template <int THREADS>
+__device__ __forceinline__ void finish_step(const TrainParams& P, int n_w, float loss_part) {
+    const int tid = threadIdx.x;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss_part += __shfl_xor_sync(0xffffffffu, loss_part, o);
+    if ((tid & 31) == 0 && loss_part != 0.0f) atomicAdd(P.loss, loss_part);
+    __threadfence();
+    __syncthreads();
+    __shared__ unsigned int s_last;
+    if (tid == 0) s_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (P.apply_update) {
+        // torch.optim.Adam (amsgrad = False, weight_decay = 0, maximize = False)
+        const float bc1 = 1.0f - powf(P.beta1, (float)P.step), bc2 = 1.0f - powf(P.beta2, (float)P.step);
+        const float step_size = P.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+        for (int i = tid; i < n_w; i += THREADS) {
+            const float g = __ldcg(P.grad + i);
+            const float m = P.beta1 * P.adam_m[i] + (1.0f - P.beta1) * g;
+            const float v = P.beta2 * P.adam_v[i] + (1.0f - P.beta2) * g * g;
+            P.adam_m[i] = m; P.adam_v[i] = v;
+            P.weights[i] -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + P.eps);
+            P.grad[i] = 0.0f;
+        }
+    }
+    if (tid == 0) *P.ticket = 0u;
+}
+
 template <int H, int ROWS>
 __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainParams P) {
     extern __shared__ __align__(16) float smem[];
@@ -300,31 +330,145 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
     }
     flush_outer<ROWS, 1>(2, H, gout, P.grad + in_dim * H + (L - 1) * H * H);
 
-    // ---- loss, then Adam by the last CTA -------------------------------------------------------------------------
+    finish_step<ROWS>(P, n_w, loss_acc * inv_n);
+}
+
+// ------------------------------------------------------------------------------------------------
+// pretrain stage: negative log-likelihood of the base distribution (disk_domain_sampling.py:14-33,
+// spherical_domain_sampling.py:16-35):  loss = -mean(D_base.log_prob(omega_o, omega_i));  Adam.
+// Base net 14 -> 16 -> 4 with biases (model.py:374-398 disk, :277-317 spherical); parameters in the 308-float base-blob
+// order W1 [16,14], b1 [16], Wo [4,16], bo [4].  Same structure as the flow kernel: thread <-> row forward / backward,
+// the parameter gradients as tile products [16 x rows] . [rows x 15] (PE3 + a ones column for the bias) and
+// [4 x rows] . [rows x 17], summed in registers over the CTA's tiles.
+// ------------------------------------------------------------------------------------------------
+// d/dx log I0(x) with the polynomials of torch.distributions.von_mises._log_modified_bessel_fn(order=0)
+__device__ __forceinline__ float dlog_i0(float x) {
+    if (x < 3.75f) {
+        const float y = (x / 3.75f) * (x / 3.75f);
+        const float c[7] = {1.0f, 3.5156229f, 3.0899424f, 1.2067492f, 0.2659732f, 0.360768e-1f, 0.45813e-2f};
+        float r = c[6], dr = 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
-    if ((tid & 31) == 0 && loss_acc != 0.0f) atomicAdd(P.loss, loss_acc * inv_n);      // mean over [N,2]: sum / (2N), 0.5 folded above
-    __threadfence();
+        for (int i = 5; i >= 0; --i) { dr = fmaf(dr, y, r); r = fmaf(r, y, c[i]); }
+        return dr / r * (2.0f * x / (3.75f * 3.75f));
+    }
+    const float y = 3.75f / x;
+    const float c[9] = {0.39894228f, 0.1328592e-1f, 0.225319e-2f, -0.157565e-2f, 0.916281e-2f, -0.2057706e-1f,
+                        0.2635537e-1f, -0.1647633e-1f, 0.392377e-2f};
+    float r = c[8], dr = 0.0f;
+#pragma unroll
+    for (int i = 7; i >= 0; --i) { dr = fmaf(dr, y, r); r = fmaf(r, y, c[i]); }
+    return 1.0f - 0.5f / x + dr / r * (-3.75f / (x * x));
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(ROWS) base_nll_step_kernel(const TrainParams P) {
+    constexpr int RS = ROWS + 4;
+    __shared__ __align__(16) float Wb[kBaseFloats + 4];
+    __shared__ __align__(16) float E[15 * RS], Hc[17 * RS], DZ[16 * RS], DP[4 * RS];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kBaseFloats; i += ROWS) Wb[i] = P.weights[i];
     __syncthreads();
-    __shared__ unsigned int s_last;
-    if (tid == 0) s_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (P.apply_update) {
-        // torch.optim.Adam (amsgrad = False, weight_decay = 0, maximize = False)
-        const float bc1 = 1.0f - powf(P.beta1, (float)P.step), bc2 = 1.0f - powf(P.beta2, (float)P.step);
-        const float step_size = P.lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
-        for (int i = tid; i < n_w; i += ROWS) {
-            const float g = __ldcg(P.grad + i);
-            const float m = P.beta1 * P.adam_m[i] + (1.0f - P.beta1) * g;
-            const float v = P.beta2 * P.adam_v[i] + (1.0f - P.beta2) * g * g;
-            P.adam_m[i] = m; P.adam_v[i] = v;
-            P.weights[i] -= step_size * m / (sqrtf(v) * inv_sqrt_bc2 + P.eps);
-            P.grad[i] = 0.0f;
+    const long long n = P.n, n_tiles = (n + ROWS - 1) / ROWS;
+    const float inv_n = 1.0f / (float)n;
+    float loss_acc = 0.0f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};               // work item tid: < 64 -> dW1/db1 item, 64..83 -> dWo/dbo item
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long i = tile * ROWS + tid;
+        const bool valid = i < n;
+        const long long ic = valid ? i : n - 1;
+        const float2 x = reinterpret_cast<const float2*>(P.x1)[ic];
+        const float2 wi = reinterpret_cast<const float2*>(P.wi)[ic];
+        float e[kPE3];
+        positional_encoding<3>(wi.x, wi.y, e);
+        float z[16], pr[4] = {Wb[304], Wb[305], Wb[306], Wb[307]};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            float a = Wb[224 + j];
+#pragma unroll
+            for (int k = 0; k < kPE3; ++k) a = fmaf(e[k], Wb[j * kPE3 + k], a);
+            z[j] = a;
+            const float h = a * sigmoid_precise(a);
+            Hc[j * RS + tid] = h;
+            pr[0] = fmaf(h, Wb[240 + j], pr[0]); pr[1] = fmaf(h, Wb[256 + j], pr[1]);
+            pr[2] = fmaf(h, Wb[272 + j], pr[2]); pr[3] = fmaf(h, Wb[288 + j], pr[3]);
+        }
+        Hc[16 * RS + tid] = 1.0f;
+#pragma unroll
+        for (int k = 0; k < kPE3; ++k) E[k * RS + tid] = e[k];
+        E[14 * RS + tid] = 1.0f;
+        // log-density and its gradient w.r.t. the four outputs
+        float lp, g[4];
+        if (P.domain == kDisk) {
+            const float s0 = expf(pr[2]), s1 = expf(pr[3]);
+            const float e0 = (x.x - pr[0]) / s0, e1 = (x.y - pr[1]) / s1;
+            lp = -kLog2Pi - (pr[2] + pr[3]) - 0.5f * (e0 * e0 + e1 * e1);
+            g[0] = e0 / s0; g[1] = e1 / s1; g[2] = e0 * e0 - 1.0f; g[3] = e1 * e1 - 1.0f;
+        } else {
+            const float ex = expf(pr[1]), sc = ex + 1e-3f;
+            const float ee = (x.x - pr[0]) / sc;
+            const float kappa = softplus_torch(pr[3]) + 1e-3f;
+            float sn, cs;
+            sincosf(x.y - pr[2], &sn, &cs);
+            lp = -0.5f * kLog2Pi - pr[1] - 0.5f * ee * ee + kappa * cs - kLog2Pi - log_i0(kappa);
+            g[0] = ee / sc;
+            g[1] = ee * ee * ex / sc - 1.0f;
+            g[2] = kappa * sn;
+            g[3] = (cs - dlog_i0(kappa)) * (pr[3] > 20.0f ? 1.0f : sigmoid_precise(pr[3]));
+        }
+        const float wgt = valid ? -inv_n : 0.0f;          // loss = -mean(logp)
+        if (valid) loss_acc -= lp;
+        float dh[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dh[j] = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float d = g[c] * wgt;
+            DP[c * RS + tid] = d;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dh[j] = fmaf(Wb[240 + c * 16 + j], d, dh[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float sg = sigmoid_precise(z[j]);
+            DZ[j * RS + tid] = dh[j] * sg * fmaf(z[j], 1.0f - sg, 1.0f);
+        }
+        __syncthreads();
+        if (tid < 64) tile_outer_one<ROWS, RS>(DZ, E, 15, tid, acc);                // [16] x [15]: kb = 4 -> 64 items
+        else if (tid < 84) tile_outer_one<ROWS, RS>(DP, Hc, 17, tid - 64, acc);     // [4] x [17]:  kb = 5 -> 20 items
+        __syncthreads();
+    }
+    // this CTA's sums -> global gradient in blob order
+    if (tid < 64) {
+        const int j = tid / 4, kq = tid % 4;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int k = kq + 4 * b;
+            if (k < 14) atomicAdd(P.grad + j * kPE3 + k, acc[b]);
+            else if (k == 14) atomicAdd(P.grad + 224 + j, acc[b]);
+        }
+    } else if (tid < 84) {
+        const int o = tid - 64, c = o / 5, kq = o % 5;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int k = kq + 5 * b;
+            if (k < 16) atomicAdd(P.grad + 240 + c * 16 + k, acc[b]);
+            else if (k == 16) atomicAdd(P.grad + 304 + c, acc[b]);
         }
     }
-    if (tid == 0) *P.ticket = 0u;
+    finish_step<ROWS>(P, kBaseFloats, loss_acc * inv_n);
+}
+
+int launch_base_nll_step(const TrainParams& P, cudaStream_t stream) {
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    auto kern = base_nll_step_kernel<128>;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 128, 0) != cudaSuccess || occ < 1) return -3;
+    long long tiles = (P.n + 127) / 128, grid = (long long)sms * occ;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 128, 0, stream>>>(P);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
 template <int H, int ROWS>

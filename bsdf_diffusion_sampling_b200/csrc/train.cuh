@@ -23,5 +23,6 @@ struct TrainParams {
 };
 
 int launch_flow_matching_step(const TrainParams& P, cudaStream_t stream);
+int launch_base_nll_step(const TrainParams& P, cudaStream_t stream);      // weights = the 308-float base blob, x1 = omega_o
 
 }  // namespace bsdfdiff

@@ -126,6 +126,75 @@ class FlowMatchingTrainer:
         return self._packed
 
 
+class BasePretrainer:
+    """Pretrain stage (disk_domain_sampling.py:14-33, spherical_domain_sampling.py:16-35): maximum likelihood of the base
+    distribution, ``loss = -mean(D_base.log_prob(omega_o, omega_i))`` with Adam (lr 3e-4 in the reference), one launch per
+    step (``bsdfdiff_base_nll_step``).  The master weights are the 308-float base blob the sampler kernels read."""
+
+    def __init__(self, base308, domain: int, lr: float = 3e-4, betas=(0.9, 0.999), eps: float = 1e-8, device="cuda"):
+        b = torch.as_tensor(base308).detach().to(torch.float32).reshape(-1)
+        if b.numel() != _lib.BASE_FLOATS:
+            raise ValueError(f"the base net is {_lib.BASE_FLOATS} floats (14 -> 16 -> 4 with biases), got {b.numel()}")
+        if domain not in (_lib.DISK, _lib.SPHERICAL):
+            raise ValueError("domain must be DISK or SPHERICAL")
+        dev = torch.device(device)
+        self.domain = int(domain)
+        self.weights = b.to(dev).contiguous().clone()
+        self.grad, self.m, self.v = (torch.zeros_like(self.weights) for _ in range(3))
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.steps = 0
+        self._ticket = torch.zeros(4, dtype=torch.int32, device=dev)
+
+    @classmethod
+    def from_module(cls, module: torch.nn.Module, domain: int, **kw) -> "BasePretrainer":
+        sd = module.state_dict()
+        flat = torch.cat([sd[k].detach().reshape(-1).float().cpu() for k in
+                          ("linear1.weight", "linear1.bias", "output.weight", "output.bias")])
+        return cls(flat, domain, **kw)
+
+    def _launch(self, omega_o, omega_i, apply_update: bool) -> torch.Tensor:
+        dev = self.weights.device
+        omega_o, omega_i = (t.detach().to(dev, torch.float32).contiguous() for t in (omega_o, omega_i))
+        n = omega_o.shape[0]
+        if n < 1 or tuple(omega_o.shape) != (n, 2) or tuple(omega_i.shape) != (n, 2):
+            raise ValueError("omega_o and omega_i must both have shape (n, 2), n >= 1")
+        if not omega_o.is_cuda:
+            raise RuntimeError("bsdfdiff.training: expected CUDA tensors; this package has no CPU path")
+        loss = torch.empty((), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = _lib.lib.bsdfdiff_base_nll_step(self.domain, n, omega_o.data_ptr(), omega_i.data_ptr(),
+                                                 self.weights.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(),
+                                                 self.v.data_ptr(), self.lr, self.betas[0], self.betas[1], self.eps,
+                                                 self.steps + 1, 1 if apply_update else 0, loss.data_ptr(),
+                                                 self._ticket.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "bsdfdiff_base_nll_step")
+        return loss
+
+    def step(self, omega_o: torch.Tensor, omega_i: torch.Tensor) -> torch.Tensor:
+        loss = self._launch(omega_o, omega_i, True)
+        self.steps += 1
+        return loss
+
+    def loss_and_grad(self, omega_o, omega_i):
+        self.grad.zero_()
+        loss = self._launch(omega_o, omega_i, False)
+        g = self.grad.clone()
+        self.grad.zero_()
+        return loss, g
+
+    def blob(self) -> torch.Tensor:
+        """The 308-float device blob ``ops.sample`` / ``NeuralBSDFSampler`` take as ``base`` (live view of the weights)."""
+        return self.weights
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        w = self.weights
+        return {"linear1.weight": w[:224].view(16, 14).clone(), "linear1.bias": w[224:240].clone(),
+                "output.weight": w[240:304].view(4, 16).clone(), "output.bias": w[304:308].clone()}
+
+    def save(self, path: str) -> None:
+        torch.save({k: v.cpu() for k, v in self.state_dict().items()}, path)
+
+
 def diffusion_stage_step(trainer: FlowMatchingTrainer, base_blob: torch.Tensor, brdf_samples: torch.Tensor,
                          batch: int, generator: Optional[torch.Generator] = None) -> torch.Tensor:
     """One iteration of ``diffusion_stage`` (disk_domain_sampling.py:46-58) on device-resident data: draw the batch rows
@@ -138,4 +207,4 @@ def diffusion_stage_step(trainer: FlowMatchingTrainer, base_blob: torch.Tensor, 
     return trainer.step(x_0, omega_o, omega_i)
 
 
-__all__ = ["FlowMatchingTrainer", "diffusion_stage_step"]
+__all__ = ["FlowMatchingTrainer", "BasePretrainer", "diffusion_stage_step"]

@@ -212,6 +212,14 @@ int bsdfdiff_flow_matching_step(int domain, int hidden, int n_hidden, int64_t n,
                                 float* adam_v, float lr, float beta1, float beta2, float eps, int64_t step,
                                 int apply_update, float* loss_out, void* sync_scratch, void* cuda_stream);
 
+/* Pretrain stage (disk_domain_sampling.py:14-33, spherical_domain_sampling.py:16-35): loss = -mean(D_base.log_prob(x, wi))
+ * over the batch, gradient w.r.t. the 308 base-net parameters (blob order W1 [16,14], b1 [16], Wo [4,16], bo [4]), Adam --
+ * one launch, same buffer contract as bsdfdiff_flow_matching_step (base_params are the fp32 master weights). */
+int bsdfdiff_base_nll_step(int domain, int64_t n, const float* x /*[n,2] omega_o*/, const float* wi /*[n,2] omega_i*/,
+                           float* base_params, float* grad, float* adam_m, float* adam_v, float lr, float beta1,
+                           float beta2, float eps, int64_t step, int apply_update, float* loss_out, void* sync_scratch,
+                           void* cuda_stream);
+
 /* ---- measured-BSDF ground truth: Mitsuba 3 `measured` eval of an RGL tensor file, and the plugins' weight + firefly clamp ----
  * Replaces  self.bsdf.eval(ctx, si, bs.wo)  (mi.load_dict({"type": "measured", ...}), rendering/brdf_measured_disk.py:36-42,92
  * and rendering/brdf_measured_spherical.py:45-51,100) and the Dr.Jit<->torch round trips of the firefly clamp

@@ -81,5 +81,44 @@ def main():
         print(name, "n =", n, "losses", losses, "->", path, os.path.getsize(path), "bytes")
 
 
+def pretrain():
+    """Pretrain-stage fixtures: the reference's base nets, -mean(log_prob) + autograd + Adam(lr 3e-4), 3 steps."""
+    sys.path.insert(0, os.path.join(REF, "learning_repo_cleanup"))
+    import utils.model as M  # noqa
+    for name, make, n in (("base_disk", lambda: M.NN_cond_pretrain_disk_one(input_dim=2, N_NEURONS=16, POSITIONAL_ENCODING_BASIS_NUM=3), 4099),
+                          ("base_spherical", lambda: M.NN_cond_pretrain_spherical_one(input_dim=2, N_NEURONS=16, POSITIONAL_ENCODING_BASIS_NUM=3), 4099)):
+        torch.manual_seed(4321)
+        net = make()
+        with torch.no_grad():                       # spread the predicted parameters (kappa on both sides of 3.75)
+            net.output.bias.add_(torch.tensor([0.1, -0.3, 0.2, 1.5]))
+            net.output.weight.mul_(3.0)
+        g = torch.Generator().manual_seed(7)
+        if name == "base_disk":
+            omega_i = torch.rand(n, 2, generator=g) * 1.2 - 0.6
+            omega_o = torch.rand(n, 2, generator=g) * 1.6 - 0.8
+        else:
+            omega_i = torch.stack([torch.rand(n, generator=g) * 1.5, torch.rand(n, generator=g) * 6.2 - 3.1], 1)
+            omega_o = torch.stack([torch.rand(n, generator=g) * 1.5, torch.rand(n, generator=g) * 6.2 - 3.1], 1)
+        order = ("linear1.weight", "linear1.bias", "output.weight", "output.bias")
+        flat = lambda sd: np.concatenate([sd[k].detach().numpy().ravel() for k in order])
+        w_before = flat(net.state_dict())
+        opt = torch.optim.Adam(net.parameters(), lr=0.0003)
+        losses, grad = [], None
+        for it in range(3):
+            logp = net.log_prob(omega_o, omega_i)
+            loss = -torch.mean(logp)
+            loss.backward()
+            if it == 0:
+                grad = flat({k: dict(net.named_parameters())[k].grad for k in order})
+            losses.append(float(loss.detach()))
+            opt.step()
+            net.zero_grad()
+        path = os.path.join(OUT, "train", f"train_{name}.npz")
+        np.savez_compressed(path, w=w_before, g=grad, w_after=flat(net.state_dict()), omega_o=omega_o.numpy(),
+                            omega_i=omega_i.numpy(), losses=np.array(losses, np.float64))
+        print(name, "losses", losses, "->", path)
+
+
 if __name__ == "__main__":
     main()
+    pretrain()

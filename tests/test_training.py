@@ -14,7 +14,8 @@ import torch
 
 from conftest import GOLDEN_DIR
 
-TRAIN_FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "train", "train_*.npz")))
+TRAIN_FILES = sorted(f for f in glob.glob(os.path.join(GOLDEN_DIR, "train", "train_*.npz")) if "train_base_" not in f)
+BASE_FILES = sorted(glob.glob(os.path.join(GOLDEN_DIR, "train", "train_base_*.npz")))
 
 
 def ids():
@@ -22,8 +23,8 @@ def ids():
 
 
 def test_train_fixtures_present():
-    assert len(TRAIN_FILES) == 3
-    for f in TRAIN_FILES:
+    assert len(TRAIN_FILES) == 3 and len(BASE_FILES) == 2
+    for f in TRAIN_FILES + BASE_FILES:
         z = np.load(f)
         assert z["losses"].shape == (3,) and np.all(np.diff(z["losses"]) < 0)      # Adam on a fixed batch: the loss goes down
 
@@ -125,3 +126,45 @@ def test_diffusion_stage_loop_reduces_the_loss(built_lib):
     assert torch.isfinite(x).all() and torch.isfinite(pdf).all()
     # samples moved from the base distribution towards the lobe
     assert float((x - 0.6 * wi[:4096]).pow(2).mean()) < float((wi[:4096] * 0).add(1).mean())
+
+
+def test_pretrainer_host_checks(built_lib):
+    B = built_lib.training.BasePretrainer
+    z = np.load(BASE_FILES[0])
+    t = B(z["w"], 0, device="cpu")
+    assert list(t.state_dict().keys()) == ["linear1.weight", "linear1.bias", "output.weight", "output.bias"]
+    assert t.state_dict()["linear1.weight"].shape == (16, 14) and t.blob().numel() == 308
+    net = built_lib.model.NN_cond_pretrain_disk_one(input_dim=2, N_NEURONS=16, POSITIONAL_ENCODING_BASIS_NUM=3)
+    net.load_state_dict(t.state_dict())
+    assert torch.equal(B.from_module(net, 0, device="cpu").weights, t.weights)
+    with pytest.raises(ValueError):
+        B(np.zeros(300, np.float32), 0, device="cpu")
+    with pytest.raises(ValueError):
+        B(z["w"], 2, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        t.step(torch.zeros(4, 2), torch.zeros(4, 2))
+    assert built_lib._lib.lib.bsdfdiff_base_nll_step(0, 16, None, 1, 1, 1, 1, 1, 3e-4, 0.9, 0.999, 1e-8, 1, 1, 1, 1, None) == -1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", BASE_FILES, ids=[os.path.basename(f)[6:-4] for f in BASE_FILES])
+def test_base_nll_step_matches_reference_autograd(built_lib, path):
+    """Pretrain stage: -mean(log_prob) of the reference's base nets (disk Gaussian; spherical Gaussian x von Mises incl.
+    the derivative of torch's log I0 polynomials and of softplus), its gradient, and three Adam(lr 3e-4) steps."""
+    z = np.load(path)
+    domain = 0 if "disk" in path else 1
+    omega_o, omega_i = torch.from_numpy(z["omega_o"]).cuda(), torch.from_numpy(z["omega_i"]).cuda()
+    tr = built_lib.training.BasePretrainer(z["w"], domain, lr=0.0003)
+    loss, g = tr.loss_and_grad(omega_o, omega_i)
+    assert abs(float(loss) - z["losses"][0]) <= 2e-6 * abs(z["losses"][0])
+    err = np.abs(g.cpu().numpy() - z["g"])
+    assert err.max() <= 3e-5 * np.abs(z["g"]).max(), (err.max(), np.abs(z["g"]).max())
+    for k in range(3):
+        loss = tr.step(omega_o, omega_i)
+        assert abs(float(loss) - z["losses"][k]) <= 3e-6 * abs(z["losses"][k]), (k, float(loss), z["losses"][k])
+    assert np.abs(tr.weights.cpu().numpy() - z["w_after"]).max() <= 2e-6
+    assert float(tr.grad.abs().max()) == 0.0
+    # the trained blob is what the sampler kernels take as `base`; log_prob through the library agrees with the loss
+    lp = built_lib.ops.base_log_prob(omega_o, omega_i, tr.blob(), domain)
+    nxt, _ = tr.loss_and_grad(omega_o, omega_i)
+    assert abs(float(-lp.mean()) - float(nxt)) <= 1e-5 * abs(float(nxt))
