@@ -13,7 +13,7 @@ __all__ = []
 if "bsdf_diffusion_sampling_b200.build" not in getattr(_sys, "orig_argv", []):
     # (`python -m bsdf_diffusion_sampling_b200.build` must be able to run when the library is missing or stale)
     from . import _lib  # noqa: F401  (raises ImportError if libbsdfdiff.so is missing)
-    from . import ops, weights, model, mlp_brdf_sampling, reflow, measured, plugins, sharding, training, materials  # noqa: F401
+    from . import ops, weights, model, mlp_brdf_sampling, reflow, measured, plugins, sharding, training, materials, mcmc  # noqa: F401
     from .mlp_brdf_sampling import (  # noqa: F401
         network_sampling_disk, network_sampling_disk_tiny, network_pdf_disk,
         network_sampling_spherical, network_pdf_spherical,
@@ -21,7 +21,7 @@ if "bsdf_diffusion_sampling_b200.build" not in getattr(_sys, "orig_argv", []):
     from .ops import set_default_precision  # noqa: F401
 
     __all__ = [
-        "ops", "weights", "model", "mlp_brdf_sampling", "reflow", "plugins", "sharding", "training", "materials",
+        "ops", "weights", "model", "mlp_brdf_sampling", "reflow", "plugins", "sharding", "training", "materials", "mcmc",
         "network_sampling_disk", "network_sampling_disk_tiny", "network_pdf_disk",
         "network_sampling_spherical", "network_pdf_spherical", "set_default_precision",
     ]
