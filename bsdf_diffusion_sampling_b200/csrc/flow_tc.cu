@@ -830,15 +830,22 @@ __device__ __forceinline__ void raw_load(const FlowParams& P, long long i, RawIn
 }
 
 // ------------------------------------------------------------------------------------------------
-// The kernel.  Warp roles (one persistent CTA per SM, 16 warps):
-//   warps 0..11   three worker groups of 4 warps; thread <-> TMEM lane <-> query row of the group's current tile.
-//                 They run nothing but the T-step flow: activation math between tensor-core round trips.
-//   warps 12..15  the producer group; thread <-> query row.  It runs one tile ahead of the workers and does all
-//                 per-query set-up that needs no tensor core: wi (and wo / replayed noise) loads, PE5(wi), the
-//                 base net, the Philox base sample and its density.  Records go through a shared-memory ring
-//                 (full/empty mbarriers).  This work is latency-bound (global loads, 10 serial Philox rounds,
-//                 serial FMA chains); on its own warps it fills the issue slots the workers leave idle while they
-//                 wait for MMAs instead of adding ~1/3 to every tile's critical path (profiles/r1d vs r1h).
+// The kernel.  Warp roles (one persistent CTA per SM, kTcThreads = 640 threads = 20 warps in the shipped build):
+//   warps 0..15   four worker groups of 4 warps (kGroups = 4); thread <-> TMEM lane <-> query row of the group's current
+//                 128-query tile, group g owns TMEM columns [128 g, 128 g + 128).  They run nothing but the T-step flow:
+//                 activation math between tensor-core round trips; warp 4 g issues group g's MMAs.
+//   warps 16..19  the producer group; thread <-> query row.  It runs up to two tiles ahead of the workers and does all
+//                 per-query set-up that needs no tensor core: wi (and wo / replayed noise / renderer uniforms) loads,
+//                 PE5(wi), the base net, the Philox base sample and its density.  Records go through a 6-slot shared-memory
+//                 ring (full/empty mbarriers).  This work is latency-bound (global loads, 10 serial Philox rounds, serial
+//                 FMA chains); on its own warps it fills the issue slots the workers leave idle while they wait for MMAs
+//                 instead of adding ~1/3 to every tile's critical path (profiles/r1d vs r1h).
+//   MULTI         one wavefront, several materials (multi.cu): the tile list is the plan's virtual-tile table, every group
+//                 keeps its own weight image in shared memory and re-stages it (one cp.async.bulk) when its next tile's
+//                 material differs; the producer re-stages the base net and passes each row's wavefront index through
+//                 the ring.
+// (tuning builds: BSDFDIFF_TC_GROUPS = 1..5, BSDFDIFF_TC_NOALIAS = the 144-column map with three groups, BSDFDIFF_TC_DUO =
+//  two groups x two tiles per thread)
 // ------------------------------------------------------------------------------------------------
 template <int DOMAIN, int MODE, int ACT, int H, bool MULTI>
 __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams P) {

@@ -46,26 +46,30 @@ __global__ void __launch_bounds__(kPlanThreads) multi_count_kernel(const int* __
         if (h[i]) atomicAdd(&counts[i], h[i]);
 }
 
-// segment offsets + the virtual-tile table (one block; M <= 255 and n / 128 tiles are small work)
+// segment offsets + the virtual-tile table.  Every block redoes the (tiny) scan over the materials in shared memory and
+// writes its own slice of the tile table, so the table of a 16 M-row wavefront (131 K tiles) is not one block's job.
 __global__ void __launch_bounds__(kPlanThreads) multi_tiles_kernel(long long n, int M, const unsigned int* __restrict__ counts,
                                                                   unsigned int* __restrict__ seg_off,
                                                                   unsigned int* __restrict__ n_tiles, int4* __restrict__ tiles) {
-    __shared__ unsigned int off[kMaxMaterials + 2], toff[kMaxMaterials + 1];
+    __shared__ unsigned int cnt[kMaxMaterials + 1], off[kMaxMaterials + 2], toff[kMaxMaterials + 1];
+    for (int i = threadIdx.x; i < M; i += kPlanThreads) cnt[i] = counts[i];
+    __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int a = 0, t = 0;
         for (int m = 0; m < M; ++m) {
             off[m] = a; toff[m] = t;
-            a += counts[m];
-            t += (counts[m] + 127u) / 128u;
+            a += cnt[m];
+            t += (cnt[m] + 127u) / 128u;
         }
         off[M] = a; off[M + 1] = (unsigned int)n; toff[M] = t;
-        *n_tiles = t;
+        if (blockIdx.x == 0) *n_tiles = t;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i <= M + 1; i += kPlanThreads) seg_off[i] = off[i];
+    if (blockIdx.x == 0)
+        for (int i = threadIdx.x; i <= M + 1; i += kPlanThreads) seg_off[i] = off[i];
     const unsigned int total = toff[M];
-    for (unsigned int j = threadIdx.x; j < total; j += kPlanThreads) {
-        int lo = 0, hi = M - 1;                         // last material whose first tile is <= j and that has tiles
+    for (unsigned int j = blockIdx.x * kPlanThreads + threadIdx.x; j < total; j += gridDim.x * kPlanThreads) {
+        int lo = 0, hi = M - 1;                         // last material whose first tile is <= j (it has tiles: see below)
         while (lo < hi) {
             const int mid_ = (lo + hi + 1) >> 1;
             if (toff[mid_] <= j) lo = mid_; else hi = mid_ - 1;
@@ -146,7 +150,9 @@ int launch_multi_plan(long long n, const int* material_id, int M, void* scratch,
     const long long per_block = kPlanThreads * kPlanItems;
     const unsigned int blocks = (unsigned int)((n + per_block - 1) / per_block);
     if (blocks) multi_count_kernel<<<blocks, kPlanThreads, 0, stream>>>(material_id, n, M, v.counts);
-    multi_tiles_kernel<<<1, kPlanThreads, 0, stream>>>(n, M, v.counts, v.seg_off, v.n_tiles, v.tiles);
+    const unsigned int tile_blocks = (unsigned int)((n / 128 + M + kPlanThreads - 1) / kPlanThreads);
+    multi_tiles_kernel<<<tile_blocks < 1 ? 1 : (tile_blocks > 296 ? 296 : tile_blocks), kPlanThreads, 0, stream>>>(
+        n, M, v.counts, v.seg_off, v.n_tiles, v.tiles);
     if (blocks) multi_scatter_kernel<<<blocks, kPlanThreads, 0, stream>>>(material_id, n, M, v.seg_off, v.cursor, v.perm);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }

@@ -904,3 +904,37 @@ def test_16M_queries_properties(pkg, prec):
     ok = pdf > 0
     area = (wo[ok, 2] / pdf[ok]).double().sum().item() / n           # pdf_omega = pdf_xy * cos  ->  1/pdf_xy = cos/pdf_omega
     assert 0.5 < area < 1.15 * np.pi
+
+
+def test_16M_row_multi_material_wavefront(pkg):
+    """Full-size wavefront with 12 materials in one launch: the plan is a permutation with 131 K+ virtual tiles, every
+    active row gets a unit direction and a finite pdf, inactive rows are zero, two runs agree bit for bit, and a strided
+    sample of rows equals the single-material calls on those rows (Philox counter = wavefront row)."""
+    files = [f for f in GOLDEN_FILES if os.path.basename(f).startswith("disk_")]
+    mats = []
+    for j in range(12):
+        flow, base, _ = O.load_material_npz(files[j % len(files)])
+        mats.append(pkg.plugins.NeuralBSDFSampler("disk", pkg.weights.pack_flow_layers(flow.layers, "cuda"),
+                                                  pkg.weights.pack_base_arrays(base.w1, base.b1, base.wo, base.bo, "cuda")))
+    mm = pkg.plugins.MultiMaterialSampler(mats)
+    n_side = 4096
+    n = n_side * n_side
+    wi = cu(O.stratified_wi_disk(n_side))
+    wi3 = torch.cat([wi, torch.sqrt(torch.clamp(1 - (wi * wi).sum(1, keepdim=True), min=0))], 1).contiguous()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    mid = torch.randint(-1, 12, (n,), device="cuda", dtype=torch.int32, generator=g)          # -1: inactive lanes
+    plan = mm.plan(mid)
+    counts = plan.counts()
+    assert int(counts.sum()) == n and torch.equal(counts[:12].cpu(), torch.bincount(mid[mid >= 0].long(), minlength=12).cpu().int())
+    wo, pdf = mm.sample(wi3, plan=plan, seed=42)
+    act = mid >= 0
+    nrm = (wo[act] * wo[act]).sum(1)
+    assert torch.allclose(nrm, torch.ones_like(nrm), atol=1e-5) and torch.isfinite(pdf).all()
+    assert (wo[~act] == 0).all() and (pdf[~act] == 0).all()
+    wo2, pdf2 = mm.sample(wi3, mid, seed=42)                                                  # a freshly built plan
+    assert torch.equal(wo, wo2) and torch.equal(pdf, pdf2)
+    idx = torch.arange(0, n, 4099, device="cuda")
+    for m in (0, 7):
+        sel = idx[mid[idx] == m]
+        ref_wo, ref_pdf = mats[m].sample(wi3[: int(sel.max()) + 1], seed=42)
+        assert torch.equal(wo[sel], ref_wo[sel]) and torch.equal(pdf[sel], ref_pdf[sel])
