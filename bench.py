@@ -452,6 +452,23 @@ def main():
                       "note": "synthetic wavefront (Mitsuba is absent): one bounce of every pixel's path per pass; the "
                               "reference runs the same two calls as ~700 eager launches + 4 Dr.Jit<->torch crossings per pass"})
 
+        # ---- one diffusion / rectify-stage iteration at the reference's batch (4.9 M rows), fused launch ----
+        n_tr = 4_900_000
+        gt = torch.Generator(device=dev).manual_seed(11 + rank)
+        om_i = torch.rand(n_tr, 2, device=dev, generator=gt) * 1.2 - 0.6
+        om_o = torch.rand(n_tr, 2, device=dev, generator=gt) * 1.6 - 0.8
+        x_b = om_i * 0.5 + 0.3 * torch.randn(n_tr, 2, device=dev, generator=gt)
+        lay, _ = load_fixture("disk")
+        trainer = pkg.training.FlowMatchingTrainer(lay, lr=1e-3, device=dev)
+        ms_tr = timed(lambda: trainer.step(x_b, om_o, om_i), 5, warm=2)
+        extra.append({"workload": "training step: diffusion / rectify stage body (forward + backward + Adam, one launch), "
+                                  "4.9 M rows, 32-wide disk flow net, fp32", "mode": "train", "value": world * n_tr / (ms_tr * 1e-3),
+                      "unit": "rows/s", "ms_per_step": ms_tr,
+                      "algorithmic_tflops": n_tr * 3 * 2 * (25 * 32 + 2 * 1024 + 64) / (ms_tr * 1e-3) / 1e12,
+                      "note": "CUDA-core kernel (train.cu); the reference's eager PyTorch step on the same GPU: "
+                              "profiles/r2i_train_bench.jsonl"})
+        del trainer, om_i, om_o, x_b
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -1125,6 +1125,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         uint32_t wpar = 0;
         int trace_r = 0;
         (void)trace_r;
+#ifdef BSDFDIFF_TC_STAGGER_NS
+        // tuning build: start the groups out of phase (group g waits g * STAGGER ns before its first tile)
+        if (g > 0) asm volatile("nanosleep.u32 %0;" ::"r"((unsigned)(g * BSDFDIFF_TC_STAGGER_NS)) : "memory");
+#endif
 
 #pragma unroll 1
         for (long long k = g; k < my_tiles; k += kGroups) {
