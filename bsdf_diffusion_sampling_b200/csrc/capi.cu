@@ -225,22 +225,23 @@ static int dispatch_fixup(int precision, FlowParams P, cudaStream_t stream, floa
     const bool tc = (precision == BSDFDIFF_PREC_TC16 || precision == BSDFDIFF_PREC_TC16_EXP);
     if (!(thr > 0.0f) || !tc || P.T == 0) return dispatch(precision, P, stream);
     if (!scratch || P.n > 0xffffffffll) return BSDFDIFF_EINVAL;
-    if (P.mode == kModeSample && !P.x0 && !P.out_x0) return BSDFDIFF_EINVAL;   // the fix-up pass replays the base sample
     P.fix_thr = thr;
     P.fix_count = static_cast<unsigned int*>(scratch);
     P.fix_list = P.fix_count + 4;
+    if (P.mode == kModeSample) P.fix_x0 = reinterpret_cast<float*>(P.fix_list + ((P.n + 1) & ~1ll));   // 8-byte aligned float2 list
     if (cudaMemsetAsync(P.fix_count, 0, 16, stream) != cudaSuccess) return fail_cuda();
     int rc = dispatch(precision, P, stream);
     if (rc != BSDFDIFF_OK) return rc;               // errors, and the fp32 reroute (nothing left to fix)
     FlowParams Q = P;
     Q.fix_pass = 1;
-    if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; Q.u_noise = nullptr; }
+    Q.out_x0 = nullptr;                      // (the tensor-core launch already reported every row's base sample)
     rc = launch_fp32(Q, stream);
     if (rc == -3) return fail_cuda();
     return rc;
 }
 
-extern "C" size_t bsdfdiff_fixup_scratch_bytes(int64_t n) { return n < 0 ? 0 : 16 + sizeof(unsigned int) * (size_t)n; }
+// [count u32, pad to 16 B][row list u32 x n, padded to an even count][base samples of the listed rows float2 x n]
+extern "C" size_t bsdfdiff_fixup_scratch_bytes(int64_t n) { return n < 0 ? 0 : 16 + 4 * (((size_t)n + 1) & ~(size_t)1) + 8 * (size_t)n; }
 
 static int fill_shape(FlowParams& P, const void* flow_packed, int domain, int hidden, int n_hidden) {
     if ((hidden != 32 && hidden != 64) || n_hidden < 1 || n_hidden > 16) return BSDFDIFF_EUNSUPPORTED;
@@ -368,7 +369,7 @@ static int dispatch_multi(int precision, FlowParams P, int n_materials, const vo
     const bool fix = tc && thr > 0.0f;
     if (fix) {
         P.fix_thr = thr; P.fix_count = v.fix_count; P.fix_list = v.fix_list;
-        if (P.mode == kModeSample && !P.x0 && !P.out_x0) P.out_x0 = v.x0;     // the fix-up pass replays the base sample
+        if (P.mode == kModeSample) P.fix_x0 = v.x0;                          // base samples of the flagged rows, next to the list
         if (cudaMemsetAsync(v.fix_count, 0, sizeof(unsigned int) * 256, stream) != cudaSuccess) return fail_cuda();
     }
     int rc = tc ? launch_tc(P, stream, precision) : launch_fp32(P, stream);
@@ -381,7 +382,7 @@ static int dispatch_multi(int precision, FlowParams P, int n_materials, const vo
     } else if (fix && rc == 0) {
         FlowParams Q = P;
         Q.fix_pass = 1;
-        if (P.mode == kModeSample) { Q.x0 = P.x0 ? P.x0 : P.out_x0; Q.out_x0 = nullptr; Q.u_noise = nullptr; }
+        Q.out_x0 = nullptr;
         rc = launch_fp32(Q, stream);
     }
     if (rc == -3) return fail_cuda();

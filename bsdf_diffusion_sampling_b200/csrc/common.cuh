@@ -88,6 +88,9 @@ struct FlowParams {
     float fix_thr;                // 0 = off
     unsigned int* fix_count;      // device counter (zeroed by the caller before the tensor-core launch)
     unsigned int* fix_list;       // device list, capacity n
+    float* fix_x0;                // [n,2] base samples of the flagged rows, parallel to fix_list (sample mode): the tensor-core
+                                  // kernel stores them next to the row index, the fix-up pass replays them -- no [n,2]
+                                  // side buffer of ALL base samples is written just to recompute a few rows
     int fix_pass;                 // 1: this launch IS the fix-up pass (flow_simt_kernel walks fix_list)
     int log_output;               // pdf mode, T == 0, raw epilogue: store log p_base instead of p_base (D_base.log_prob)
     // one wavefront, several materials: rows are bucketed by material ON THE DEVICE (multi.cu) into

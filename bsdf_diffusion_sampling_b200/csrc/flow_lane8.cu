@@ -37,7 +37,8 @@ __device__ __forceinline__ void silu_grad8(float z, float& h, float& g) {
 // `act` = the group's row in shared memory.  All eight lanes carry the scalar state redundantly.
 template <bool TANGENTS>
 __device__ __forceinline__ void lane8_row(const FlowParams& P, const float* __restrict__ W, const float* __restrict__ base,
-                                          float* __restrict__ act, int sub, unsigned mask, long long i) {
+                                          float* __restrict__ act, int sub, unsigned mask, long long i,
+                                          const float2* __restrict__ x0_fix) {
     const int k0 = (P.domain == kDisk) ? 3 : 4;      // first PE column of layer 1
     const float inv_t = (float)(1.0 / (double)P.T);
     const int j0 = 4 * sub;
@@ -98,7 +99,10 @@ __device__ __forceinline__ void lane8_row(const FlowParams& P, const float* __re
         theta_o = x0;
     } else {
         if (base) base_eval8();
-        if (P.x0) {
+        if (x0_fix) {                                  // fix-up pass: the base sample the tensor-core kernel stored with the row
+            const float2 t = *x0_fix;
+            x0 = t.x; x1 = t.y;
+        } else if (P.x0) {
             const float2 t = reinterpret_cast<const float2*>(P.x0)[i];
             x0 = t.x; x1 = t.y;
         } else {
@@ -261,11 +265,12 @@ __global__ void __launch_bounds__(kL8Threads) flow_lane8_kernel(const FlowParams
     long long jj = (long long)blockIdx.x * kL8Rows + slot;
     unsigned int k = blockIdx.x;
     int m = 0;
+    const bool x0_listed = P.fix_pass && P.fix_x0 && P.mode == kModeSample;
     for (;;) {
-        long long i = -1;
+        long long i = -1, at = 0;                        // at = position in the fix-up list (base samples are stored alongside)
         if (!multi) {
             if ((long long)(jj - slot) >= n_rows) break;         // uniform over the CTA
-            if (jj < n_rows) i = P.fix_pass ? (long long)P.fix_list[jj] : jj;
+            if (jj < n_rows) { i = P.fix_pass ? (long long)P.fix_list[jj] : jj; at = jj; }
             jj += (long long)gridDim.x * kL8Rows;
         } else if (!P.fix_pass) {
             if (k >= n_work) break;
@@ -279,10 +284,11 @@ __global__ void __launch_bounds__(kL8Threads) flow_lane8_kernel(const FlowParams
             if (m >= P.n_materials) break;
             need(m);
             const unsigned int e = k * kL8Rows + slot;
-            if (e < P.fix_count[m]) i = (long long)P.fix_list[P.seg_off[m] + e];
+            if (e < P.fix_count[m]) { at = (long long)P.seg_off[m] + e; i = (long long)P.fix_list[at]; }
             k += gridDim.x;
         }
-        if (i >= 0) lane8_row<TANGENTS>(P, W, bptr, act, sub, mask, i);
+        if (i >= 0) lane8_row<TANGENTS>(P, W, bptr, act, sub, mask, i,
+                                        x0_listed ? reinterpret_cast<const float2*>(P.fix_x0) + at : nullptr);
     }
 }
 

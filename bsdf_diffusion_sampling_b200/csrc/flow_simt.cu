@@ -123,7 +123,7 @@ __device__ __forceinline__ void velocity(const float* __restrict__ W, int domain
 // The whole flow of one query (row i of the caller's tensors) with the staged weight set.
 template <int H, bool TANGENTS>
 __device__ __forceinline__ void simt_row(const FlowParams& P, const float* __restrict__ W, const float* __restrict__ base,
-                                         Act<H, TANGENTS> a, long long i) {
+                                         Act<H, TANGENTS> a, long long i, const float2* __restrict__ x0_fix) {
     const int k0 = (P.domain == kDisk) ? 3 : 4;      // first PE column of layer 1
     const float inv_t = (float)(1.0 / (double)P.T);
     float w0, w1, wiz;
@@ -151,7 +151,10 @@ __device__ __forceinline__ void simt_row(const FlowParams& P, const float* __res
         theta_o = x0;
     } else {
         if (base) base_eval(base, w0, w1, bp);
-        if (P.x0) {
+        if (x0_fix) {                                  // fix-up pass: the base sample stored with the flagged row
+            const float2 t = *x0_fix;
+            x0 = t.x; x1 = t.y;
+        } else if (P.x0) {
             float2 t = reinterpret_cast<const float2*>(P.x0)[i];
             x0 = t.x; x1 = t.y;
         } else {
@@ -242,11 +245,13 @@ __global__ void __launch_bounds__(kThreads) flow_simt_kernel(const FlowParams P)
     long long jj = (long long)blockIdx.x * kThreads + threadIdx.x;       // single
     unsigned int k = blockIdx.x;                                         // multi main: tile; multi fix: chunk of material m
     int m = 0;
+    const bool x0_listed = P.fix_pass && P.fix_x0 && P.mode == kModeSample;
     for (;;) {
-        long long i = -1;
+        long long i = -1, at = 0;
         if (!multi) {
             if (jj >= n_rows) break;
             i = P.fix_pass ? (long long)P.fix_list[jj] : jj;
+            at = jj;
             jj += (long long)gridDim.x * kThreads;
         } else if (!P.fix_pass) {
             if (k >= n_tiles) break;
@@ -259,10 +264,11 @@ __global__ void __launch_bounds__(kThreads) flow_simt_kernel(const FlowParams P)
             if (m >= P.n_materials) break;
             need(m);
             const unsigned int e = k * kThreads + threadIdx.x;
-            if (e < P.fix_count[m]) i = (long long)P.fix_list[P.seg_off[m] + e];
+            if (e < P.fix_count[m]) { at = (long long)P.seg_off[m] + e; i = (long long)P.fix_list[at]; }
             k += gridDim.x;
         }
-        if (i >= 0) simt_row<H, TANGENTS>(P, W, bptr, a, i);
+        if (i >= 0) simt_row<H, TANGENTS>(P, W, bptr, a, i,
+                                          x0_listed ? reinterpret_cast<const float2*>(P.fix_x0) + at : nullptr);
     }
 }
 

@@ -498,16 +498,21 @@ __device__ __forceinline__ void base_draw_fast(const float p[4], unsigned long l
 // Multi-material launches keep one list per material (a warp's rows share a tile, hence a material): material m's
 // list lives at fix_list[seg_off[m] ...] -- it can never outgrow the material's own row count -- with its length in
 // fix_count[m], so the fix-up pass can stage one weight set per chunk of rows.
-__device__ __forceinline__ void flag_for_fixup(const FlowParams& P, bool flag, long long i, int mat = -1) {
+__device__ __forceinline__ void flag_for_fixup(const FlowParams& P, bool flag, long long i, int mat = -1,
+                                               float x0_init = 0.0f, float x1_init = 0.0f) {
     const uint32_t mask = __ballot_sync(0xffffffffu, flag);
     if (mask == 0u) return;
     const int lane = threadIdx.x & 31;
     unsigned int* count = (mat >= 0) ? P.fix_count + mat : P.fix_count;
-    unsigned int* list = (mat >= 0) ? P.fix_list + P.seg_off[mat] : P.fix_list;
+    const unsigned int seg = (mat >= 0) ? P.seg_off[mat] : 0u;
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(count, (unsigned int)__popc(mask));
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (flag) list[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned int)i;
+    if (flag) {
+        const unsigned int at = seg + base + __popc(mask & ((1u << lane) - 1u));
+        P.fix_list[at] = (unsigned int)i;
+        if (P.fix_x0) reinterpret_cast<float2*>(P.fix_x0)[at] = make_float2(x0_init, x1_init);   // the base sample to replay
+    }
 }
 
 struct TcSmem {
@@ -783,7 +788,7 @@ __device__ __forceinline__ void publish_and_issue_duo(TcSmem& S, int pipe, int q
 
 // Per-thread state of one of the two tiles a duo worker thread owns.
 struct Pipe {
-    float x0, x1, R, p0, theta_o;
+    float x0, x1, R, p0, theta_o, x1_start;
     CondTrack cond;
     long long k;            // index of the tile in this CTA's tile list (k % kGroups == pipe)
     int sl;                 // ring slot of tile k
@@ -1038,7 +1043,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                     const float (*f)[kTile] = S.slot[p.sl];
                     if (MODE == kModeSample) {
                         if (valid) store_sample<true>(P, i, p.x0, p.x1, p.p0 * p.R);
-                        if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && p.cond.weight() < P.fix_thr, i);
+                        if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && p.cond.weight() < P.fix_thr, i, -1, p.theta_o, p.x1_start);
                     } else if (MODE == kModePdf) {
                         float bp[4];
 #pragma unroll
@@ -1071,7 +1076,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 const float (*f)[kTile] = S.slot[p.sl];
                 p.x0 = f[kFX][row]; p.x1 = f[kFX + 1][row];
                 p.p0 = (MODE == kModeSample) ? f[kFP0][row] : 1.0f;
-                p.theta_o = p.x0;
+                p.theta_o = p.x0; p.x1_start = p.x1;
                 p.R = 1.0f;
                 p.cond.reset();
                 p.t = 0;
@@ -1091,7 +1096,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         pa.k = g;            pa.sl = g;            pa.alive = pa.k < my_tiles;
         pb.k = g + kWGroups; pb.sl = g + kWGroups; pb.alive = pb.k < my_tiles;
         pa.use = pb.use = 0u; pa.pd = pb.pd = 0u; pa.rounds = pb.rounds = 0u; pa.phase = pb.phase = -1; pa.t = pb.t = 0;
-        pa.x0 = pa.x1 = pb.x0 = pb.x1 = 0.0f; pa.R = pb.R = pa.p0 = pb.p0 = 1.0f; pa.theta_o = pb.theta_o = 0.0f;
+        pa.x0 = pa.x1 = pb.x0 = pb.x1 = 0.0f; pa.R = pb.R = pa.p0 = pb.p0 = 1.0f; pa.theta_o = pb.theta_o = 0.0f; pa.x1_start = pb.x1_start = 0.0f;
         pa.cond.reset(); pb.cond.reset();
         int skew = BSDFDIFF_TC_SKEW;
 #pragma unroll 1
@@ -1167,7 +1172,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 i_raw = idx;
             }
             const long long i = valid ? i_raw : (MULTI ? 0 : P.n - 1);
-            const float theta_o = x0;
+            const float theta_o = x0, x1_start = x1;          // start state: pdf-mode mask / the base sample a fix-up replays
 
 #pragma unroll 1
             for (int t = 0; t < P.T; ++t) {
@@ -1214,7 +1219,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
             if (MODE == kModeSample) {
                 if (valid) store_sample<true>(P, i, x0, x1, p0 * R);
-                if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && cond.weight() < P.fix_thr, i, MULTI ? mat : -1);
+                if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && cond.weight() < P.fix_thr, i, MULTI ? mat : -1, theta_o, x1_start);
             } else if (MODE == kModePdf) {
                 float bp[4];
 #pragma unroll

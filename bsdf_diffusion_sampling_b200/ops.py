@@ -118,7 +118,7 @@ def _sample_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: torch.
     out_dir = torch.empty((n, 2 if epilogue == EPI_RAW else 3), dtype=torch.float32, device=wi.device)
     out_pdf = torch.empty((n,), dtype=torch.float32, device=wi.device)
     scratch = _fix_scratch(n, wi.device, precision, fix_thr, T)
-    need_x0 = want_x0 or (scratch is not None and x0 is None)      # the fix-up pass replays the base sample
+    need_x0 = want_x0
     out_x0 = torch.empty((n if need_x0 else 0, 2), dtype=torch.float32, device=wi.device)
     with torch.cuda.device(wi.device):
         rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
@@ -147,19 +147,15 @@ def _sample_out_op(wi: torch.Tensor, flow_blob: Optional[torch.Tensor], base: to
                    precision: int, domain: int, epilogue: int, T: int, hidden: int, n_hidden: int,
                    seed: int, offset: int, first_index: int, fix_thr: float) -> None:
     """As ``bsdfdiff::sample`` but writes into caller-owned buffers (no allocation: streaming pipelines).
-    ``scratch`` (int32, >= 4 + 3 n elements) enables the fix-up: [count, pad x3][row list n][base sample 2 n]."""
+    ``scratch`` (int32, ``sample_scratch_elems(n)`` elements) enables the fix-up: [count, pad x3][row list n, even-padded][base samples of the listed rows 2 n]."""
     n = wi.shape[0]
     fix = scratch is not None and fix_thr > 0.0 and precision != PREC_FP32 and T > 0
-    x0_side = None
-    if fix and x0 is None:
-        x0_side = scratch[4 + n:4 + 3 * n].view(torch.float32)
     with torch.cuda.device(wi.device):
         rc = _lib.lib.bsdfdiff_sample(precision, domain, epilogue, T, n, wi.data_ptr(),
                                       flow_blob.data_ptr() if flow_blob is not None else None,
                                       hidden, n_hidden, base.data_ptr(), x0.data_ptr() if x0 is not None else None,
                                       u.data_ptr() if u is not None else None,
-                                      seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(),
-                                      x0_side.data_ptr() if x0_side is not None else None,
+                                      seed, offset, first_index, out_dir.data_ptr(), out_pdf.data_ptr(), None,
                                       fix_thr if fix else 0.0, scratch.data_ptr() if fix else None, _stream(wi))
     _lib.check(rc, "bsdfdiff_sample")
 
@@ -251,13 +247,12 @@ def _sample_planar_op(wx: torch.Tensor, wy: torch.Tensor, wz: torch.Tensor, flow
     n = wx.shape[0]
     ox, oy, oz, pdf = (torch.empty((n,), dtype=torch.float32, device=wx.device) for _ in range(4))
     scratch = _fix_scratch(n, wx.device, precision, fix_thr, T)
-    side = torch.empty((n if (scratch is not None and x0 is None) else 0, 2), dtype=torch.float32, device=wx.device)
     with torch.cuda.device(wx.device):
         rc = _lib.lib.bsdfdiff_sample_planar(precision, domain, epilogue, T, n, _ptr3(wx, wy, wz), flow_blob.data_ptr(),
                                              hidden, n_hidden, base.data_ptr(),
                                              x0.data_ptr() if x0 is not None else None,
                                              u.data_ptr() if u is not None else None, seed, offset, first_index,
-                                             _ptr3(ox, oy, oz), pdf.data_ptr(), side.data_ptr() if side.numel() else None,
+                                             _ptr3(ox, oy, oz), pdf.data_ptr(), None,
                                              fix_thr if scratch is not None else 0.0,
                                              scratch.data_ptr() if scratch is not None else None, _stream(wx))
     _lib.check(rc, "bsdfdiff_sample_planar")
@@ -551,7 +546,7 @@ def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int 
 
 def sample_scratch_elems(n: int) -> int:
     """int32 elements of the scratch buffer ``sample_into`` needs for ``n`` rows when the fix-up is on."""
-    return 4 + 3 * int(n)
+    return 4 + ((int(n) + 1) & ~1) + 2 * int(n)
 
 
 def sample_into(wi: torch.Tensor, flow, base: torch.Tensor, T: int, out_dir: torch.Tensor, out_pdf: torch.Tensor, *,

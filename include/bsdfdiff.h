@@ -114,11 +114,12 @@ int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
  * stated pdf tolerance -- an ideal fp16-operand / fp32-accumulate evaluation misses it too (profiles/r2_emulate_tc16.txt).
  * With fix_threshold > 0 the tensor-core kernel computes, per query, the conditioning weight
  *     w = min(1, min_t|det_t| / 0.2) * min(1, 16 / prod_t max(1, sigma_max(J_t))) [* min(1, 25 / |grad log p_base|), pdf()]
- * and appends every row with w < fix_threshold to a device list; a second launch on the same stream recomputes
- * exactly those rows with the PREC_FP32 kernel (same base sample: x0_replay, or out_x0, one of which is then
- * REQUIRED for bsdfdiff_sample).  No host synchronisation; CUDA-graph capturable (memset + 2 kernels).
- * fix_scratch: device buffer of bsdfdiff_fixup_scratch_bytes(n) bytes; after the call its first uint32 holds the
- * number of recomputed rows.  fix_threshold = 0 (or PREC_FP32): single launch, scratch may be NULL. */
+ * and appends every row with w < fix_threshold -- and, for bsdfdiff_sample, the base sample it started from -- to a
+ * device list; a second launch on the same stream recomputes exactly those rows with the PREC_FP32 kernel from the same
+ * base sample.  No host synchronisation; CUDA-graph capturable (memset + 2 kernels).
+ * fix_scratch: device buffer of bsdfdiff_fixup_scratch_bytes(n) ~ 16 + 12 n bytes ([count][row list][base samples of the
+ * listed rows]); after the call its first uint32 holds the number of recomputed rows.  fix_threshold = 0 (or
+ * PREC_FP32): single launch, scratch may be NULL. */
 size_t bsdfdiff_fixup_scratch_bytes(int64_t n);
 
 /* ---- pdf: reverse flow from wo; pdf = p_base(x_T | wi) * prod det(I - dD/dx / T) ---------------------------- */
