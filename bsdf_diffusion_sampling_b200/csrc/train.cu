@@ -490,7 +490,10 @@ static int launch_train_t(const TrainParams& P, cudaStream_t stream) {
 
 int launch_flow_matching_step(const TrainParams& P, cudaStream_t stream) {
     if (P.n_hidden < 1) return -2;
-    if (P.hidden == 32) return P.n_hidden <= 4 ? launch_train_t<32, 128>(P, stream) : -2;
+    // 32-wide nets: 128-row tiles while two CTAs fit an SM (3 hidden layers: 111 KB each); with 4 hidden layers a 128-row
+    // CTA needs 133 KB (one per SM), 96-row tiles need 104 KB (two per SM: 6 warps instead of 4)
+    if (P.hidden == 32) return P.n_hidden <= 3 ? launch_train_t<32, 128>(P, stream)
+                             : P.n_hidden == 4 ? launch_train_t<32, 96>(P, stream) : -2;
     if (P.hidden == 64 && P.n_hidden > 6) return -2;
     // 64-wide nets: the z columns of 6 layers + 89 KB of weights only fit with 32-row tiles
     if (P.hidden == 64) return P.n_hidden <= 4 ? launch_train_t<64, 64>(P, stream) : launch_train_t<64, 32>(P, stream);
