@@ -93,9 +93,19 @@ constexpr int kWGroups = kDuo ? kGroups / 2 : kGroups;   // worker thread groups
 #ifndef BSDFDIFF_TC_SKEW
 #define BSDFDIFF_TC_SKEW 2       // turns by which a thread's second tile trails its first (so their short output passes do not meet)
 #endif
+// BSDFDIFF_TC_ISSUER (tuning build): one dedicated MMA-issuer warp per group.  Worker warps never block in a barrier:
+// they bar.arrive in the middle of an activation pass (first 16 neurons stored and every accumulator read) and at its
+// end; the group's issuer warp bar.syncs on the same named barriers and issues K-chunk 0 of the next round's u and z
+// MMAs under the workers' second-half math, the rest (+ commit) at the end.  24 warps -> 80 registers per thread.
+#ifndef BSDFDIFF_TC_ISSUER
+#define BSDFDIFF_TC_ISSUER 0
+#endif
+constexpr bool kIssuer = BSDFDIFF_TC_ISSUER != 0;
+static_assert(!kIssuer || (!kDuo && BSDFDIFF_TC_GROUPS == 4), "issuer warps: the four-group, one-tile-per-thread structure");
 constexpr int kWorkerThreads = kWGroups * 128;
 constexpr int kProducerWarps = 4;                  // one 128-thread producer group: thread <-> query row of a tile
-constexpr int kTcThreads = kWorkerThreads + 32 * kProducerWarps;
+constexpr int kIssuerWarps = kIssuer ? kGroups : 0;
+constexpr int kTcThreads = kWorkerThreads + 32 * kProducerWarps + 32 * kIssuerWarps;
 #ifndef BSDFDIFF_TC_SLOTS
 #define BSDFDIFF_TC_SLOTS (BSDFDIFF_TC_GROUPS + 2)
 #endif
@@ -580,6 +590,52 @@ __device__ __forceinline__ void base_eval_smem(const TcSmem& S, const float* e, 
 // tangents use hi only.  type 0: first layer (tangent seeds are K=16 operands in A_u/A_v chunk 0),
 // 1..NH-1: hidden layer, NH: output layer (N = 16, fp32 accumulators throughout).
 // Order: u, z, v -- A_u is read first and D_v (which overlaps A_u) is written last.
+// Split issue of one round (issuer-warp builds; 32-wide tangent rounds, aliased TMEM map): PART 1 = K-chunk 0 of the u and z
+// products (their operands are complete once the first 16 neurons of the previous pass are stored; D_u and D_z have been
+// read by then), PART 2 = everything else + commit.  Order inside PART 2: u (chunk 1) before the v products, which write
+// D_v over A_u.  The first-layer round (type 0) has no early part: its operand is written in one go.
+template <int PART>
+__device__ __forceinline__ void issue_round_split(int type, int NH, uint32_t tg, uint64_t b_first, uint64_t b_out, uint32_t bar) {
+    constexpr int H = 32;
+    constexpr uint32_t idz = make_idesc(H, true), idt = make_idesc(H, false), ido = make_idesc(16, true);
+    constexpr uint32_t kChunk = (2u * H * 16u) >> 4, kLoHid = (H * H * 2u) >> 4;
+    constexpr uint32_t kFirstBytes = 2u * H * 32u * 2u, kHidBytes = 2u * H * H * 2u;
+    constexpr uint32_t kChunkOut = (2u * 16u * 16u) >> 4, kLoOut = (16u * H * 2u) >> 4;
+    const uint32_t a = tg + col_ah<H>();
+    if (type < NH) {                                 // hidden layer (type >= 1 here)
+        const uint64_t b = b_first + (uint64_t)((kFirstBytes >> 4) + (uint32_t)(type - 1) * (kHidBytes >> 4));
+        if (PART == 1) {
+            mma_ts<0>(tg + kColDu, tg + kColAu, b, idt);
+            mma_ts<0>(tg + kColDz, a, b, idz);
+            mma_ts<1>(tg + kColDz, a, b + kLoHid, idz);
+        } else {
+            mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunk, idt);
+            mma_ts<1>(tg + kColDz, a + 8, b + kChunk, idz);
+            mma_ts<1>(tg + kColDz, a + 8, b + kLoHid + kChunk, idz);
+            mma_ts<0>(tg + kColDv, tg + kColAv, b, idt);
+            mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + kChunk, idt);
+        }
+    } else {                                         // output layer, N = 16, fp32 accumulators
+        const uint64_t b = b_out;
+        if (PART == 1) {
+            mma_ts<0>(tg + kColDu, tg + kColAu, b, ido);
+            mma_ts<0>(tg + kColDz, a, b, ido);
+            mma_ts<1>(tg + kColDz, a, b + kLoOut, ido);
+        } else {
+            mma_ts<1>(tg + kColDu, tg + kColAu + 8, b + kChunkOut, ido);
+            mma_ts<1>(tg + kColDz, a + 8, b + kChunkOut, ido);
+            mma_ts<1>(tg + kColDz, a + 8, b + kLoOut + kChunkOut, ido);
+            mma_ts<0>(tg + kColDv, tg + kColAv, b, ido);
+            mma_ts<1>(tg + kColDv, tg + kColAv + 8, b + kChunkOut, ido);
+        }
+    }
+    if (PART == 2) tc_commit(bar);
+}
+// named barriers of the issuer-warp builds: 1 + g = "first half stored" (mid), 5 + g = "pass stored" (end); 160 = the group's
+// 128 worker threads (bar.arrive) + its issuer warp (bar.sync)
+__device__ __forceinline__ void issuer_arrive(int id) { asm volatile("bar.arrive %0, 160;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void issuer_sync(int id) { asm volatile("bar.sync %0, 160;" ::"r"(id) : "memory"); }
+
 template <bool TANGENTS, int H>
 __device__ __forceinline__ void issue_round(int type, int NH, uint32_t tg, uint64_t b_first, uint64_t b_out, uint64_t av_desc,
                                             uint32_t bar) {
@@ -664,6 +720,7 @@ __device__ __forceinline__ void publish_and_issue(int g, int q, int type, int NH
     tc_wait_st();
     tc_fence_before();
     TC_TRACE(4);
+    if (kIssuer && TANGENTS && H == 32) { issuer_arrive(5 + g); return; }      // the group's issuer warp takes it from here
     group_sync(g);
     TC_TRACE(5);
     if (q == 0) {
@@ -711,7 +768,7 @@ __device__ __forceinline__ void build_first_operand(const float (*f)[kTile], int
 // fp16) -> h = silu(z), u = s2 du, v = s2 dv -> fp16 operand words of the next round (tcgen05.st).  The second half of the
 // accumulators streams in under the first half's math.
 template <bool TANGENTS, int ACT, int H>
-__device__ __forceinline__ void activation_pass(uint32_t tg, uint32_t av_row, int trace_r = 0) {
+__device__ __forceinline__ void activation_pass(uint32_t tg, uint32_t av_row, int trace_r = 0, int g = 0) {
     if (H != 32) {
         // wide forward-only round: H / 16 chunks of 16 neurons, the next chunk's load in flight
         float zc[2][16];
@@ -743,6 +800,11 @@ __device__ __forceinline__ void activation_pass(uint32_t tg, uint32_t av_row, in
     }
     tc_wait_ld();
     TC_TRACE(2);
+    if (BSDFDIFF_TC_ISSUER == 1 && TANGENTS) {     // first half stored, every accumulator of the round read: chunk 0 may go
+        tc_wait_st();
+        tc_fence_before();
+        issuer_arrive(1 + g);
+    }
     activate16<TANGENTS, ACT>(zb, ub, vb, ph, pu, pv);
     tmem_st8(tg + col_ah<H>() + 8, ph);
     if (TANGENTS) {
@@ -907,7 +969,61 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
     // tile list of this CTA: blockIdx.x, +gridDim.x, ...; entry k goes to group k % kGroups through slot k % kSlots
     const long long my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    if (warp >= kWGroups * 4) {
+    if (kIssuer && warp >= kWGroups * 4 + kProducerWarps) {
+        // =========================== MMA issuer of group g (tuning build) ================================
+        if (TANGENTS && H == 32) {
+            const int g = warp - (kWGroups * 4 + kProducerWarps);
+            const uint32_t tg_mma = tmem_base + g * kColsPerGroup;
+            const uint32_t bar_d = smem_u32(&S.d_ready[g]);
+            const uint32_t w_base = smem_u32(S.w16) + (MULTI ? (uint32_t)g * img_bytes : 0u);
+            const uint64_t b_hid0 = make_b_desc(w_base, H * 16, 128);
+            uint64_t b_out = make_b_desc(w_base + 2u * H * 32u * 2u + (uint32_t)(NH - 1) * (2u * H * H * 2u), 256, 128);
+            asm volatile("" : "+l"(b_out));
+            int mat_staged = -1;
+            uint32_t wpar = 0;
+            if (!MULTI) mbar_wait(smem_u32(&S.w_bar[0]), 0);
+#pragma unroll 1
+            for (long long k = g; k < my_tiles; k += kGroups) {
+#pragma unroll 1
+                for (int t = 0; t < P.T; ++t) {
+                    issuer_sync(5 + g);                       // the step's first-layer operand is stored
+                    if (MULTI && t == 0) {
+                        // (every MMA of the group's previous tile has completed: its workers waited for the last round before
+                        // they built this operand)
+                        const int mat = P.tiles[blockIdx.x + k * gridDim.x].x;
+                        if (mat != mat_staged) {
+                            if (elect_one()) {
+                                const unsigned char* blob = P.flows[mat];
+                                const PackedHeader* h2 = reinterpret_cast<const PackedHeader*>(blob);
+                                mbar_expect_tx(smem_u32(&S.w_bar[g]), h2->f16_bytes);
+                                tma_bulk_g2s(w_base, blob + h2->off_f16, h2->f16_bytes, smem_u32(&S.w_bar[g]));
+                            }
+                            __syncwarp();
+                            mbar_wait(smem_u32(&S.w_bar[g]), wpar); wpar ^= 1u;
+                            mat_staged = mat;
+                        }
+                    }
+                    if (elect_one()) { tc_fence_after(); issue_round<TANGENTS, H>(0, NH, tg_mma, b_hid0, b_out, 0ull, bar_d); }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int l = 0; l < NH; ++l) {
+                        if (BSDFDIFF_TC_ISSUER == 1) {            // split issue: chunk 0 of u and z under the second half's math
+                            issuer_sync(1 + g);
+                            if (elect_one()) { tc_fence_after(); issue_round_split<1>(l + 1, NH, tg_mma, b_hid0, b_out, bar_d); }
+                            __syncwarp();
+                            issuer_sync(5 + g);
+                            if (elect_one()) { tc_fence_after(); issue_round_split<2>(l + 1, NH, tg_mma, b_hid0, b_out, bar_d); }
+                            __syncwarp();
+                        } else {                                  // == 2: dedicated issuer, whole round at the end of the pass
+                            issuer_sync(5 + g);
+                            if (elect_one()) { tc_fence_after(); issue_round<TANGENTS, H>(l + 1, NH, tg_mma, b_hid0, b_out, 0ull, bar_d); }
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp >= kWGroups * 4) {
         // =========================== producer ==========================================================
         const int row = (warp - kWGroups * 4) * 32 + lane;
         RawIn cur, nxt;
@@ -1125,7 +1241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
         uint32_t use = 0;
         const float inv_t = (float)(1.0 / (double)P.T);
         const float step = (MODE == kModePdf) ? -inv_t : inv_t;
-        if (!MULTI && q == 0) mbar_wait(smem_u32(&S.w_bar[0]), 0);              // weights have landed in smem
+        if (!(kIssuer && TANGENTS && H == 32) && !MULTI && q == 0) mbar_wait(smem_u32(&S.w_bar[0]), 0);  // weights have landed in smem
         int mat = 0, mat_staged = -1;                                           // multi: material of this tile / of the group's image
         uint32_t wpar = 0;
         int trace_r = 0;
@@ -1144,7 +1260,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 // image has completed (all four warps waited for the previous tile's last round), and only this warp
                 // issues the group's MMAs, so it alone has to see the new image land.
                 mat = P.tiles[blockIdx.x + k * gridDim.x].x;
-                if (q == 0 && mat != mat_staged) {
+                if (!(kIssuer && TANGENTS && H == 32) && q == 0 && mat != mat_staged) {
                     if (elect_one()) {
                         const unsigned char* blob = P.flows[mat];
                         const PackedHeader* h2 = reinterpret_cast<const PackedHeader*>(blob);
@@ -1192,7 +1308,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                     mbar_wait(bar_d, pd); pd ^= 1u;
                     tc_fence_after();
                     TC_TRACE(0);
-                    activation_pass<TANGENTS, ACT, H>(tg, av_row, trace_r);
+                    activation_pass<TANGENTS, ACT, H>(tg, av_row, trace_r, g);
                     publish_and_issue<TANGENTS, H>(g, q, l + 1, NH, tg_mma, b_hid0, b_out, av_desc, bar_d, trace_r);
 #ifdef BSDFDIFF_TC_TRACE
                     ++trace_r;
