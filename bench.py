@@ -277,8 +277,10 @@ def main():
     config["numa_node"] = numa if numa is not None else "not exposed (single node / VM)"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    fix_on = args.precision == "tc16" and pkg.ops.get_fixup_threshold() > 0
-    config["fixup_threshold"] = pkg.ops.get_fixup_threshold() if fix_on else 0.0
+    fix_thr = pkg.ops.default_fixup_threshold(pkg.ops.DISK if args.workload == "disk" else pkg.ops.SPHERICAL,
+                                              pkg.ops.EPI_DISK if args.workload == "disk" else pkg.ops.EPI_SPHERICAL, args.mode)
+    fix_on = args.precision == "tc16" and fix_thr > 0
+    config["fixup_threshold"] = fix_thr if fix_on else 0.0
     launches_per_step = 2 if fix_on else 1
     first_index = rank * n
 

@@ -47,7 +47,8 @@ class MaterialPack:
         self.entries: List[dict] = []
 
     # -- building --------------------------------------------------------------------------------------------------
-    def add(self, name, kind: str, flow_layers: Sequence, base308, T: Optional[int] = None) -> "MaterialPack":
+    def add(self, name, kind: str, flow_layers: Sequence, base308, T: Optional[int] = None,
+            fixup: Optional[Dict[str, float]] = None) -> "MaterialPack":
         if kind not in plugins._KINDS:
             raise ValueError(f"unknown plugin kind {kind!r}")
         layers = [np.ascontiguousarray(weights._np32(w)) for w in flow_layers]
@@ -61,8 +62,17 @@ class MaterialPack:
         if any(e["name"] == str(name) for e in self.entries):
             raise ValueError(f"material {name!r} is already in the pack")
         self.entries.append({"name": str(name), "kind": kind, "T": int(T or plugins._KINDS[kind][2]), "flow": layers,
-                             "base": base})
+                             "base": base, "fixup": None if fixup is None else {k: float(fixup[k]) for k in ("sample", "pdf")}})
         return self
+
+    def calibrate(self, device="cuda", **kw) -> Dict[str, Dict[str, float]]:
+        """Per-material fix-up thresholds of the tensor-core path (``NeuralBSDFSampler.calibrate_fixup``, needs the GPU),
+        kept in the pack: ``sampler(name)`` then recomputes in fp32 only what THIS material needs to meet the parity bars
+        instead of what the worst material of its family needs.  -> {name: {"sample": t, "pdf": t}}."""
+        for e in self.entries:
+            e["fixup"] = None
+            e["fixup"] = self.sampler(e["name"], device).calibrate_fixup(**kw)
+        return {e["name"]: dict(e["fixup"]) for e in self.entries}
 
     def add_state_dicts(self, name, kind: str, flow_sd: Dict, base_sd: Dict, T: Optional[int] = None) -> "MaterialPack":
         base = np.concatenate([weights._np32(base_sd[k]).ravel() for k in
@@ -91,6 +101,8 @@ class MaterialPack:
                 rec["flow"].append({"shape": list(w.shape), "offset": off})
                 blobs.append(w)
                 off += _pad(w.nbytes)
+            if e.get("fixup") is not None:
+                rec["fixup"] = e["fixup"]
             rec["base"] = {"offset": off}
             blobs.append(e["base"])
             off += _pad(e["base"].nbytes)
@@ -124,7 +136,7 @@ class MaterialPack:
         pack = cls()
         for rec in index["materials"]:
             layers = [arr(f["offset"], int(np.prod(f["shape"]))).reshape(f["shape"]) for f in rec["flow"]]
-            pack.add(rec["name"], rec["kind"], layers, arr(rec["base"]["offset"], 308), rec["T"])
+            pack.add(rec["name"], rec["kind"], layers, arr(rec["base"]["offset"], 308), rec["T"], rec.get("fixup"))
         return pack
 
     # -- use -------------------------------------------------------------------------------------------------------
@@ -136,6 +148,8 @@ class MaterialPack:
         if e is None:
             raise KeyError(name)
         kw.setdefault("T", e["T"])
+        if e.get("fixup") is not None:
+            kw.setdefault("fixup", dict(e["fixup"]))
         return plugins.NeuralBSDFSampler(e["kind"], weights.pack_flow_layers(e["flow"], device),
                                          torch.from_numpy(np.array(e["base"])).to(device), **kw)
 

@@ -76,18 +76,41 @@ def next_philox(device) -> Tuple[int, int]:
 
 
 # ---- conditioning-triggered fp32 fix-up of the tc16 path (include/bsdfdiff.h) ---------------------------------
-_fixup_threshold = float(os.environ.get("BSDFDIFF_FIXUP", "0.25"))
+# Default conditioning thresholds (a query whose weight w falls below is recomputed in fp32), per flow family and call:
+# the largest-waste-free values for which EVERY material the reference ships (27 measured-disk, 25 measured-spherical and
+# 25 bsdf checkpoints) meets the raw BASELINE.md section-5 bars on the shipped path -- calibrated on the measured errors of
+# the tensor-core launch (profiles/flag_dump.py + flag_study.py -> profiles/r2s_flag_study.txt, checked by
+# profiles/material_sweep.py and tests/test_all_materials.py).  One material dictates each value (disk sample:
+# ilm_solo_m_68's MEDIAN error; spherical pdf(): chm_orange's reverse, expanding flow); a material calibrated on its own
+# (plugins.NeuralBSDFSampler.calibrate_fixup, stored by materials.MaterialPack) usually needs no fix-up at all.
+_FIX_DEFAULT = {
+    ("disk", "sample"): 0.15, ("disk", "pdf"): 1.0 / 60.0,
+    ("spherical", "sample"): 0.25, ("spherical", "pdf"): 0.5,
+    ("bsdf", "sample"): 0.125, ("bsdf", "pdf"): 0.25,
+}
+_fixup_threshold: Optional[float] = (float(os.environ["BSDFDIFF_FIXUP"]) if "BSDFDIFF_FIXUP" in os.environ else None)
 _last_fix_scratch = {}
 
 
-def set_fixup_threshold(thr: float) -> None:
-    """Conditioning weight below which a tc16 query is recomputed in fp32 (0 disables the second launch)."""
+def set_fixup_threshold(thr: Optional[float]) -> None:
+    """Override the conditioning weight below which a tc16 query is recomputed in fp32 for every call that does not pass
+    ``fixup=`` (0 disables the second launch; None restores the per-family defaults)."""
     global _fixup_threshold
-    _fixup_threshold = float(thr)
+    _fixup_threshold = None if thr is None else float(thr)
 
 
-def get_fixup_threshold() -> float:
-    return _fixup_threshold
+def default_fixup_threshold(domain: int, epilogue: int = EPI_RAW, mode: str = "sample") -> float:
+    """The threshold a call without ``fixup=`` uses: the process-wide override (``set_fixup_threshold`` / BSDFDIFF_FIXUP)
+    if there is one, else the calibrated default of the flow family (raw-epilogue spherical calls cannot tell the
+    measured-spherical from the bsdf plugin and take the stricter measured-spherical value)."""
+    if _fixup_threshold is not None:
+        return _fixup_threshold
+    family = "disk" if domain == DISK else ("bsdf" if epilogue == EPI_BSDF else "spherical")
+    return _FIX_DEFAULT[(family, mode)]
+
+
+def get_fixup_threshold(domain: int = DISK, epilogue: int = EPI_RAW, mode: str = "sample") -> float:
+    return default_fixup_threshold(domain, epilogue, mode)
 
 
 def last_fixup_count(device=None) -> int:
@@ -313,7 +336,7 @@ def sample_planar(wi_xyz, flow, base: torch.Tensor, T: int, *, epilogue: int, x0
         raise ValueError("T must be >= 1")
     x0, u, seed, offset = _noise(wx.unsqueeze(1), x0, u, seed, offset)
     return _sample_planar_op(wx, wy, wz, flow.blob, base, x0, u, _resolve_precision(precision), flow.domain, epilogue,
-                             int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), _fix_thr(fixup))
+                             int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), _fix_thr(fixup, flow.domain, epilogue, "sample"))
 
 
 def pdf_planar(wo_xyz, wi_xyz, flow, base: torch.Tensor, T: int, *, epilogue: int, precision=None, fixup=None) -> torch.Tensor:
@@ -325,7 +348,7 @@ def pdf_planar(wo_xyz, wi_xyz, flow, base: torch.Tensor, T: int, *, epilogue: in
         raise ValueError("planar directions exist for the plugin epilogues only")
     _check_flow(flow, T, "pdf_planar")
     return _pdf_planar_op(ox, oy, oz, wx, wy, wz, flow.blob, base, _resolve_precision(precision), flow.domain, epilogue,
-                          int(T), flow.hidden, flow.n_hidden, _fix_thr(fixup))
+                          int(T), flow.hidden, flow.n_hidden, _fix_thr(fixup, flow.domain, epilogue, "pdf"))
 
 
 # ---- one wavefront, several materials (include/bsdfdiff.h: bsdfdiff_multi_plan / _sample_multi / _pdf_multi) ----------
@@ -462,7 +485,7 @@ def sample_multi(wi: torch.Tensor, plan: MultiPlan, table: MaterialTable, T: int
     x0, u, seed, offset = _noise(wi, x0, u, seed, offset)
     return _sample_multi_op(wi, plan.scratch, table.flow_ptrs, table.base_ptrs, x0, u, _resolve_precision(precision),
                             table.domain, epilogue, int(T), table.hidden, table.n_hidden, int(seed), int(offset),
-                            int(first_index), _fix_thr(fixup))
+                            int(first_index), _fix_thr(fixup, table.domain, epilogue, "sample"))
 
 
 def pdf_multi(wo: torch.Tensor, wi: torch.Tensor, plan: MultiPlan, table: MaterialTable, T: int, *,
@@ -475,7 +498,7 @@ def pdf_multi(wo: torch.Tensor, wi: torch.Tensor, plan: MultiPlan, table: Materi
     _check_rows(wo, wi.shape[0], cols, "wo")
     _check_multi(table, plan, wi, T, "pdf_multi")
     return _pdf_multi_op(wo, wi, plan.scratch, table.flow_ptrs, table.base_ptrs, _resolve_precision(precision),
-                         table.domain, epilogue, int(T), table.hidden, table.n_hidden, _fix_thr(fixup))
+                         table.domain, epilogue, int(T), table.hidden, table.n_hidden, _fix_thr(fixup, table.domain, epilogue, "pdf"))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -503,8 +526,11 @@ def _check_rows(t: torch.Tensor, n: int, cols: int, what: str) -> None:
         raise ValueError(f"bsdfdiff: {what} must have shape ({n}, {cols}), got {tuple(t.shape)}")
 
 
-def _fix_thr(fixup) -> float:
-    return _fixup_threshold if fixup is None else float(fixup)
+def _fix_thr(fixup, domain: int = DISK, epilogue: int = EPI_RAW, mode: str = "sample") -> float:
+    """``fixup``: None (process-wide override or the family default), a threshold, or {"sample": t, "pdf": t}."""
+    if isinstance(fixup, dict):
+        fixup = fixup.get(mode)
+    return default_fixup_threshold(domain, epilogue, mode) if fixup is None else float(fixup)
 
 
 def _noise(wi: torch.Tensor, x0, u, seed, offset):
@@ -541,7 +567,7 @@ def sample(wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int 
     x0, u, seed, offset = _noise(wi, x0, u, seed, offset)
     return _sample_op(wi, flow.blob, base, x0, u, _resolve_precision(precision), flow.domain, epilogue, int(T),
                       flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index), bool(return_x0),
-                      _fix_thr(fixup))
+                      _fix_thr(fixup, flow.domain, epilogue, "sample"))
 
 
 def sample_scratch_elems(n: int) -> int:
@@ -571,7 +597,7 @@ def sample_into(wi: torch.Tensor, flow, base: torch.Tensor, T: int, out_dir: tor
     x0, u, seed, offset = _noise(wi, x0, u, seed, offset)
     _sample_out_op(wi, flow.blob, base, x0, u, out_dir, out_pdf, scratch, _resolve_precision(precision), flow.domain,
                    epilogue, int(T), flow.hidden, flow.n_hidden, int(seed), int(offset), int(first_index),
-                   _fix_thr(fixup))
+                   _fix_thr(fixup, flow.domain, epilogue, "sample"))
 
 
 def pdf(wo: torch.Tensor, wi: torch.Tensor, flow, base: torch.Tensor, T: int, *, epilogue: int = EPI_RAW,
@@ -584,7 +610,7 @@ def pdf(wo: torch.Tensor, wi: torch.Tensor, flow, base: torch.Tensor, T: int, *,
     _check_rows(wi, wi.shape[0], cols, "wi")
     _check_rows(wo, wi.shape[0], cols, "wo")
     return _pdf_op(wo, wi, flow.blob, base, _resolve_precision(precision), flow.domain, epilogue, int(T),
-                   flow.hidden, flow.n_hidden, _fix_thr(fixup))
+                   flow.hidden, flow.n_hidden, _fix_thr(fixup, flow.domain, epilogue, "pdf"))
 
 
 def base_log_prob(x: torch.Tensor, wi: torch.Tensor, base: torch.Tensor, domain: int) -> torch.Tensor:

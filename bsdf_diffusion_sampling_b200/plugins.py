@@ -24,6 +24,7 @@ from __future__ import annotations
 import os
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 
 from . import measured as _measured
@@ -54,6 +55,26 @@ def checkpoint_paths(kind: str, material, root: str = "./checkpoints_new") -> Tu
     raise ValueError(f"unknown plugin kind {kind!r}")
 
 
+def stratified_domain_wi(kind: str, n_side: int, seed: int = 0) -> np.ndarray:
+    """``n_side^2`` jittered-grid incident directions in the plugin kind's DOMAIN coordinates [n,2] fp32: the concentric-disk
+    map scaled to r < 0.95 (the reference's generator, utils_sampling_torch_disk.py:99-114) for the disk plugin;
+    (theta, phi) with theta in (0, pi/2) for the measured-spherical plugin (spherical_domain_sampling.py:173-175) and in
+    (0, pi) for the bsdf plugin (bsdf_correct_sampling.py:174)."""
+    rng = np.random.default_rng(seed)
+    n = n_side * n_side
+    i, j = np.divmod(np.arange(n), n_side)
+    u, v = (i + rng.random(n)) / n_side, (j + rng.random(n)) / n_side
+    if kind == "disk":
+        a, b = 2 * u - 1, 2 * v - 1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            big = np.abs(a) > np.abs(b)
+            r = np.where(big, a, b)
+            phi = np.nan_to_num(np.where(big, (np.pi / 4) * (b / a), np.pi / 2 - (np.pi / 4) * (a / b)))
+        return (0.95 * np.stack([r * np.cos(phi), r * np.sin(phi)], 1)).astype(np.float32)
+    top = np.pi / 2 if kind == "spherical" else np.pi
+    return np.stack([u * top * 0.98 + 0.01 * top, v * 2 * np.pi - np.pi], 1).astype(np.float32)
+
+
 class NeuralBSDFSampler:
     """Fused sample / pdf for one material (one flow net + one base net)."""
 
@@ -69,7 +90,9 @@ class NeuralBSDFSampler:
         self.flow, self.base = flow, base
         self.T = int(T or t_default)
         self.precision = precision
-        self.fixup = fixup            # conditioning threshold of the tc16 fp32 fix-up (None: ops' default, 0: off)
+        # conditioning threshold of the tc16 fp32 fix-up: None = the flow family's default (ops._FIX_DEFAULT), 0 = off,
+        # a float, or {"sample": t, "pdf": t} (what calibrate_fixup returns and materials.MaterialPack stores)
+        self.fixup = fixup
 
     # -- construction -------------------------------------------------------------------------
     @classmethod
@@ -83,6 +106,43 @@ class NeuralBSDFSampler:
         flow = weights.pack_flow_layers(weights.flow_layers_from_state_dict(weights.load_checkpoint(fp)), device)
         base = weights.pack_base_state_dict(weights.load_checkpoint(bp), device)
         return cls(kind, flow, base, **kw)
+
+    # -- per-material fix-up thresholds ---------------------------------------------------------------
+    FIXUP_LADDER = (0.0, 1 / 64, 1 / 45, 1 / 32, 1 / 22, 1 / 16, 1 / 11, 0.125, 0.18, 0.25, 0.35, 0.5, 0.7, 1.0)
+
+    def calibrate_fixup(self, n_side: int = 256, seed: int = 11, margin: float = 0.85, install: bool = True) -> dict:
+        """Smallest fix-up thresholds of ``FIXUP_LADDER`` with which THIS material's shipped tensor-core path meets the raw
+        parity bars (times ``margin``) against the fp32 kernel on ``n_side^2`` stratified incident
+        directions: {"sample": t, "pdf": t}.  The family defaults are dictated by the worst material of a family; most
+        materials need no second launch at all.  ``install`` makes the sampler use the result."""
+        wi = torch.from_numpy(stratified_domain_wi(self.kind, n_side, seed)).to(self.base.device)
+        x32, p32, x0 = ops.sample(wi, self.flow, self.base, self.T, seed=20261018, offset=0, precision="fp32")
+        q32 = ops.pdf(x32, wi, self.flow, self.base, self.T, precision="fp32")
+        scale = x32.abs().clamp_min(1.0)
+
+        def meets(p, pr, x=None):
+            ok = torch.isfinite(pr) & (pr.abs() > 0)
+            r = ((p[ok] - pr[ok]).abs() / pr[ok].abs().clamp_min(1e-6)).nan_to_num(nan=float("inf"))
+            good = (r.median() <= 5e-3 * margin and torch.quantile(r, 0.99) <= 5e-2 * margin
+                    and (r > 0.5).float().mean() <= 1e-3 * margin)
+            if x is not None:
+                dx = ((x - x32).abs() / scale).flatten()
+                good = good and dx.median() <= 5e-4 * margin and torch.quantile(dx, 0.99) <= 1e-2 * margin
+            return bool(good)
+
+        out = {"sample": 1.0, "pdf": 1.0}
+        for t in self.FIXUP_LADDER:
+            x16, p16, _ = ops.sample(wi, self.flow, self.base, self.T, x0=x0, precision="tc16", fixup=t)
+            if meets(p16, p32, x16):
+                out["sample"] = t
+                break
+        for t in self.FIXUP_LADDER:
+            if meets(ops.pdf(x32, wi, self.flow, self.base, self.T, precision="tc16", fixup=t), q32):
+                out["pdf"] = t
+                break
+        if install:
+            self.fixup = dict(out)
+        return out
 
     # -- the two hot calls ----------------------------------------------------------------------
     def sample(self, wi: torch.Tensor, *, x0=None, u=None, seed=None, offset=0, first_index=0):
@@ -152,7 +212,8 @@ class NeuralBSDFSampler:
         in_free, out_free = pipe["in_free"], pipe["out_free"]     # slot-reuse events, kept across calls
         cur = torch.cuda.current_stream(device)
         s_k.wait_stream(cur)                 # weights / anything the caller enqueued before this call
-        fix = ops.get_fixup_threshold() > 0 and ops._resolve_precision(self.precision) != ops.PREC_FP32
+        fix = (ops._fix_thr(self.fixup, self.domain, self.epilogue, "sample") > 0
+               and ops._resolve_precision(self.precision) != ops.PREC_FP32)
         launches = 0
         for a in range(0, n, chunk):
             b, j = min(n, a + chunk), pipe["k"] % 3
@@ -171,7 +232,7 @@ class NeuralBSDFSampler:
                 if not copy_only:
                     ops.sample_into(wi_dev[: b - a], self.flow, self.base, self.T, wo_dev[: b - a], pdf_dev[: b - a],
                                     epilogue=self.epilogue, seed=seed, offset=offset, first_index=first_index + a,
-                                    precision=self.precision, scratch=scratch)
+                                    precision=self.precision, scratch=scratch, fixup=self.fixup)
                     launches += 2 if fix else 1
                 ev_k = torch.cuda.Event()
                 ev_k.record(s_k)
@@ -220,9 +281,16 @@ class MultiMaterialSampler:
             raise ValueError("need at least one material")
         s0 = self.samplers[0]
         for s in self.samplers:
-            if (s.kind, s.T, s.precision, s.fixup) != (s0.kind, s0.T, s0.precision, s0.fixup):
-                raise ValueError("all materials of one MultiMaterialSampler must share plugin kind, T, precision and fix-up threshold")
-        self.kind, self.T, self.epilogue, self.precision, self.fixup = s0.kind, s0.T, s0.epilogue, s0.precision, s0.fixup
+            if (s.kind, s.T, s.precision) != (s0.kind, s0.T, s0.precision):
+                raise ValueError("all materials of one MultiMaterialSampler must share plugin kind, T and precision")
+        self.kind, self.T, self.epilogue, self.precision = s0.kind, s0.T, s0.epilogue, s0.precision
+        # one launch, one conditioning threshold: the strictest any of the materials asks for (per-material calibrated
+        # thresholds differ; None everywhere keeps following the process-wide default)
+        if all(s.fixup is None for s in self.samplers):
+            self.fixup = None
+        else:
+            self.fixup = {m: max(ops._fix_thr(s.fixup, s.domain, s.epilogue, m) for s in self.samplers)
+                          for m in ("sample", "pdf")}
         self.table = ops.MaterialTable([s.flow for s in self.samplers], [s.base for s in self.samplers])
 
     def plan(self, material_id: torch.Tensor) -> "ops.MultiPlan":

@@ -51,7 +51,30 @@ def make(reference_root: str = "/root/reference") -> bool:
                 p = os.path.join(ck, f"{mat}_{dom}", name)
                 if os.path.exists(p):
                     shutil.copyfile(p, os.path.join(d, name))
+    make_packs(ck)
     return True
+
+
+def make_packs(ck: str) -> dict:
+    """Every material the reference ships (rendering/checkpoints_new: measured disk, measured spherical, bsdf_<k>) as three
+    .bsdfpack files under oracle/_ref/ -- input of profiles/material_sweep.py and tests/test_all_materials.py, which check the
+    shipped tensor-core path against the fp32 kernel and the oracle on ALL of them, not only on the eight goldens."""
+    repo = os.path.dirname(HERE)
+    if repo not in sys.path:
+        sys.path.insert(0, repo)
+    from bsdf_diffusion_sampling_b200 import plugins
+    from bsdf_diffusion_sampling_b200.materials import MaterialPack
+    dirs = sorted(os.listdir(ck))
+    sets = {"disk": [d[:-5] for d in dirs if d.endswith("_disk")],
+            "spherical": [d[:-10] for d in dirs if d.endswith("_spherical") and not d.startswith("bsdf_")],
+            "bsdf": sorted((d[5:-10] for d in dirs if d.startswith("bsdf_") and d.endswith("_spherical")), key=int)}
+    out = {}
+    for kind, mats in sets.items():
+        ok = [m for m in mats if all(os.path.exists(p) for p in plugins.checkpoint_paths(kind, m, ck))]
+        pack = MaterialPack.from_checkpoints(kind, ok, ck)
+        pack.save(os.path.join(OUT, f"all_{kind}.bsdfpack"))
+        out[kind] = len(ok)
+    return out
 
 
 def load(workload: str):
