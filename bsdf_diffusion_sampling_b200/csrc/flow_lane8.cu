@@ -27,8 +27,22 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
     v += __shfl_xor_sync(mask, v, 4, 8);
     return v;
 }
+// sigmoid to ~2 ulp without the IEEE division and expf's range reduction: ex2.approx (2 ulp) of a clamped argument, rcp.approx
+// plus one Newton step -- 7 instructions instead of ~25; the activation math is a quarter of this kernel's instructions
+__device__ __forceinline__ float sigmoid8(float z) {
+    float e, r;
+    const float a = fminf(z * -1.4426950408889634f, 126.0f);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
+    const float d = 1.0f + e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    return r * fmaf(-d, r, 2.0f);
+}
 __device__ __forceinline__ void silu_grad8(float z, float& h, float& g) {
+#ifdef BSDFDIFF_LANE8_IEEE
     const float s = sigmoid_precise(z);
+#else
+    const float s = sigmoid8(z);
+#endif
     h = z * s;
     g = s * fmaf(z, 1.0f - s, 1.0f);          // silu'(z) = s (1 + z (1 - s))
 }
@@ -155,15 +169,25 @@ __device__ __forceinline__ void lane8_row(const FlowParams& P, const float* __re
         const float* Wl = W + P.in_dim * kH;
         for (int l = 1; l < P.n_hidden; ++l) {
             float az[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-            for (int k = 0; k < kH; ++k) {
-                const float4 w = *reinterpret_cast<const float4*>(Wl + k * kH + j0);
-                const float hk = act[k];
-                az[0] = fmaf(hk, w.x, az[0]); az[1] = fmaf(hk, w.y, az[1]); az[2] = fmaf(hk, w.z, az[2]); az[3] = fmaf(hk, w.w, az[3]);
+            // four k per iteration: the row's h / u / v arrive as one float4 each (7 shared-memory loads per 48 FMAs instead
+            // of 16); the accumulation order over k is unchanged
+#pragma unroll 2
+            for (int k4 = 0; k4 < kH; k4 += 4) {
+                const float4 h4 = *reinterpret_cast<const float4*>(act + k4);
+                float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = u4;
                 if (TANGENTS) {
-                    const float uk = act[kH + k], vk = act[2 * kH + k];
-                    au[0] = fmaf(uk, w.x, au[0]); au[1] = fmaf(uk, w.y, au[1]); au[2] = fmaf(uk, w.z, au[2]); au[3] = fmaf(uk, w.w, au[3]);
-                    av[0] = fmaf(vk, w.x, av[0]); av[1] = fmaf(vk, w.y, av[1]); av[2] = fmaf(vk, w.z, av[2]); av[3] = fmaf(vk, w.w, av[3]);
+                    u4 = *reinterpret_cast<const float4*>(act + kH + k4);
+                    v4 = *reinterpret_cast<const float4*>(act + 2 * kH + k4);
+                }
+                const float hs[4] = {h4.x, h4.y, h4.z, h4.w}, us[4] = {u4.x, u4.y, u4.z, u4.w}, vs[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w = *reinterpret_cast<const float4*>(Wl + (k4 + q) * kH + j0);
+                    az[0] = fmaf(hs[q], w.x, az[0]); az[1] = fmaf(hs[q], w.y, az[1]); az[2] = fmaf(hs[q], w.z, az[2]); az[3] = fmaf(hs[q], w.w, az[3]);
+                    if (TANGENTS) {
+                        au[0] = fmaf(us[q], w.x, au[0]); au[1] = fmaf(us[q], w.y, au[1]); au[2] = fmaf(us[q], w.z, au[2]); au[3] = fmaf(us[q], w.w, au[3]);
+                        av[0] = fmaf(vs[q], w.x, av[0]); av[1] = fmaf(vs[q], w.y, av[1]); av[2] = fmaf(vs[q], w.z, av[2]); av[3] = fmaf(vs[q], w.w, av[3]);
+                    }
                 }
             }
             __syncwarp(mask);                         // every lane has read the layer's inputs
@@ -220,7 +244,10 @@ __device__ __forceinline__ void lane8_row(const FlowParams& P, const float* __re
 }
 
 template <bool TANGENTS>
-__global__ void __launch_bounds__(kL8Threads) flow_lane8_kernel(const FlowParams P) {
+#ifndef BSDFDIFF_L8_MINB
+#define BSDFDIFF_L8_MINB 4
+#endif
+__global__ void __launch_bounds__(kL8Threads, BSDFDIFF_L8_MINB) flow_lane8_kernel(const FlowParams P) {
     extern __shared__ __align__(16) float smem[];
     const int n_w = f32_image_floats(P.in_dim, kH, P.n_hidden);
     float* W = smem;
