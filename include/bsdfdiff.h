@@ -119,7 +119,10 @@ int bsdfdiff_sample(int precision, int domain, int epilogue, int T, int64_t n,
  * base sample.  No host synchronisation; CUDA-graph capturable (memset + 2 kernels).
  * fix_scratch: device buffer of bsdfdiff_fixup_scratch_bytes(n) ~ 16 + 12 n bytes ([count][row list][base samples of the
  * listed rows]); after the call its first uint32 holds the number of recomputed rows.  fix_threshold = 0 (or
- * PREC_FP32): single launch, scratch may be NULL. */
+ * PREC_FP32): single launch, scratch may be NULL.
+ * Thresholds with which EVERY material the reference ships meets the stated bars (calibrated on all 77 checkpoints,
+ * profiles/r2s_material_sweep.txt; the host package's defaults): disk flows 0.15 (sample) / 1/60 (pdf), measured-spherical
+ * 0.25 / 0.5, bsdf 0.125 / 0.25.  A material calibrated on its own usually needs none (0). */
 size_t bsdfdiff_fixup_scratch_bytes(int64_t n);
 
 /* ---- pdf: reverse flow from wo; pdf = p_base(x_T | wi) * prod det(I - dD/dx / T) ---------------------------- */
