@@ -16,6 +16,10 @@
 
 namespace bsdfdiff {
 
+#ifndef BSDFDIFF_L8_UNROLL
+#define BSDFDIFF_L8_UNROLL 4
+#endif
+constexpr int kL8Unroll = BSDFDIFF_L8_UNROLL;   // k-blocks of the hidden-layer product per loop iteration (tuning builds)
 constexpr int kL8Threads = 128;               // 4 warps x 4 queries
 constexpr int kL8Rows = 16;                   // queries per CTA step
 constexpr int kL8Act = 100;                   // floats per query row in shared memory: h[32] u[32] v[32] + 4 pad (bank shift 4 per row)
@@ -171,7 +175,7 @@ __device__ __forceinline__ void lane8_row(const FlowParams& P, const float* __re
             float az[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f}, av[4] = {0.f, 0.f, 0.f, 0.f};
             // four k per iteration: the row's h / u / v arrive as one float4 each (7 shared-memory loads per 48 FMAs instead
             // of 16); the accumulation order over k is unchanged
-#pragma unroll 2
+#pragma unroll kL8Unroll
             for (int k4 = 0; k4 < kH; k4 += 4) {
                 const float4 h4 = *reinterpret_cast<const float4*>(act + k4);
                 float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = u4;
