@@ -31,21 +31,11 @@ __device__ __forceinline__ float group_sum(float v, unsigned mask) {
     v += __shfl_xor_sync(mask, v, 4, 8);
     return v;
 }
-// sigmoid to ~2 ulp without the IEEE division and expf's range reduction: ex2.approx (2 ulp) of a clamped argument, rcp.approx
-// plus one Newton step -- 7 instructions instead of ~25; the activation math is a quarter of this kernel's instructions
-__device__ __forceinline__ float sigmoid8(float z) {
-    float e, r;
-    const float a = fminf(z * -1.4426950408889634f, 126.0f);
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(a));
-    const float d = 1.0f + e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
-    return r * fmaf(-d, r, 2.0f);
-}
 __device__ __forceinline__ void silu_grad8(float z, float& h, float& g) {
 #ifdef BSDFDIFF_LANE8_IEEE
     const float s = sigmoid_precise(z);
 #else
-    const float s = sigmoid8(z);
+    const float s = sigmoid_newton(z);
 #endif
     h = z * s;
     g = s * fmaf(z, 1.0f - s, 1.0f);          // silu'(z) = s (1 + z (1 - s))

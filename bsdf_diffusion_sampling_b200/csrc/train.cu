@@ -28,7 +28,7 @@
 namespace bsdfdiff {
 
 __device__ __forceinline__ void silu_both(float z, float& h, float& g) {
-    const float s = 1.0f / (1.0f + expf(-z));
+    const float s = sigmoid_newton(z);
     h = z * s;
     g = s * fmaf(z, 1.0f - s, 1.0f);
 }
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
             for (int k = 0; k < K; ++k) {
                 float hk;
                 if (l == 0) hk = IN[k * RS + tid];
-                else { const float z = zin[k * RS + tid]; hk = z / (1.0f + expf(-z)); }
+                else { const float z = zin[k * RS + tid]; hk = z * sigmoid_newton(z); }
                 const float4* w4 = reinterpret_cast<const float4*>(Wl + k * H);
 #pragma unroll
                 for (int j4 = 0; j4 < H / 4; ++j4) {
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
             const float* zl = Z + (size_t)(L - 1) * H * RS;
             for (int k = 0; k < H; ++k) {
                 const float z = zl[k * RS + tid];
-                const float h = z / (1.0f + expf(-z));
+                const float h = z * sigmoid_newton(z);
                 HP[k * RS + tid] = h;
                 const float2 w = reinterpret_cast<const float2*>(Wl)[k];
                 p0 = fmaf(h, w.x, p0); p1 = fmaf(h, w.y, p1);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
             for (int j = 0; j < H; ++j) D[j * RS + tid] = dz[j];
             const float* src = (l == 0) ? IN : Z + (size_t)(l - 1) * H * RS;
             if (l > 0) {
-                for (int k = 0; k < H; ++k) { const float z = src[k * RS + tid]; HP[k * RS + tid] = z / (1.0f + expf(-z)); }
+                for (int k = 0; k < H; ++k) { const float z = src[k * RS + tid]; HP[k * RS + tid] = z * sigmoid_newton(z); }
             }
             __syncthreads();
             // dW_l [H][K]
