@@ -291,13 +291,17 @@ def main():
             return float(t.item())
         return ms
 
-    def time_device(workload, mode, steps, warmup, want_clocks=False):
-        """(ms total, queries per GPU, last output, rows the last fix-up pass recomputed, clocks) for `steps` timed steps."""
+    def time_device(workload, mode, steps, warmup, want_clocks=False, calibrate=False):
+        """(ms total, queries per GPU, last output, rows the last fix-up pass recomputed, clocks) for `steps` timed steps.
+        calibrate: use the material's OWN fix-up thresholds (what materials.MaterialPack.calibrate stores) instead of
+        the flow family's defaults."""
         Tw = 4 if workload == "disk" else 8
         layers, base = load_fixture(workload)
         pf = pkg.weights.pack_flow_layers(layers, dev)
         pb = pkg.weights.pack_base_arrays(*base, dev)
         s = pkg.plugins.NeuralBSDFSampler(workload, pf, pb, T=Tw, precision=args.precision)
+        if calibrate:
+            s.calibrate_fixup()
         wi_np = synth_wi3(workload, n_side, seed=1000 + rank)
         wi = torch.from_numpy(wi_np).to(dev)
         wo = s.sample(wi, seed=7, first_index=first_index)[0] if mode == "pdf" else None
@@ -326,7 +330,7 @@ def main():
         if clocks:
             clocks.stop_flag = True
             clocks.join(1.0)
-        fixed = pkg.ops.last_fixup_count(dev) if fix_on else 0
+        fixed = pkg.ops.last_fixup_count(dev) if (fix_on and not (calibrate and s.fixup[mode] == 0)) else 0
         return max_ms(ms), s, wi_np, out, fixed, clocks
 
     ms, sampler, wi_np, out, fixed_rows, clocks = time_device(args.workload, args.mode, args.steps, args.warmup, True)
@@ -387,6 +391,17 @@ def main():
                           "unit": "samples/s", "ms_per_step": ms_x / ks, "steps": ks,
                           "roofline_frac": qps * Fx / 1e12 / measured_peak()[0],
                           "fixup_rows_last_step": fx})
+        # the same four calls with the material's own calibrated fix-up thresholds (a MaterialPack user's configuration)
+        for wl, md in (("disk", "sample"), ("disk", "pdf"), ("spherical", "sample"), ("spherical", "pdf")):
+            ks = max(3, min(args.steps, 5))
+            ms_x, s_x, _, _, fx, _ = time_device(wl, md, ks, 3, calibrate=True)
+            Fx = F_DISK if wl == "disk" else F_SPH
+            qps = n * ks / (ms_x * 1e-3)
+            extra.append({"workload": wl, "mode": md, "T": 4 if wl == "disk" else 8, "value": world * qps,
+                          "unit": "samples/s", "ms_per_step": ms_x / ks, "steps": ks,
+                          "roofline_frac": qps * Fx / 1e12 / measured_peak()[0], "fixup_rows_last_step": fx,
+                          "fixup": "per-material calibrated thresholds (NeuralBSDFSampler.calibrate_fixup)",
+                          "fixup_thresholds": s_x.fixup})
 
     # ---- twelve materials in ONE wavefront (disney_bsdf_array0_envmap.xml:35-335), single launch over
     #      the device-built plan vs Mitsuba's per-instance dispatch (boolean-mask gather, one launch per material, scatter)

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """What the conditioning-triggered fp32 fix-up costs per material: 16.7 M sample() queries with the bench's synthetic wi,
-tensor-core launch alone (fixup=0) vs the shipped path (threshold 0.25), rows recomputed, for every golden material.
+tensor-core launch alone (fixup=0) vs the shipped path (the flow family's default threshold) and vs the material's own
+calibrated threshold (NeuralBSDFSampler.calibrate_fixup), rows recomputed, for every golden material.
     python profiles/fixup_cost.py > profiles/<round>_fixup_cost.txt"""
 import glob
 import os
@@ -28,7 +29,7 @@ def timed(fn, steps=5, warm=2):
     return a.elapsed_time(b) / steps
 
 
-print("%-44s %5s %10s %10s %9s %10s" % ("material", "T", "tc only ms", "shipped ms", "overhead", "rows fixed"))
+print("%-44s %5s %10s %10s %9s %-22s | %s" % ("material", "T", "tc only ms", "shipped ms", "overhead", "rows fixed", "calibrated: thr, ms, rows fixed"))
 for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
     z = np.load(path)
     name = os.path.basename(path)[:-4]
@@ -39,8 +40,13 @@ for path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))):
     if kind == "bsdf":
         wi[1::2, 2] *= -1.0                                   # both hemispheres
     a = pkg.plugins.NeuralBSDFSampler(kind, pf, pb, precision="tc16", fixup=0.0)
-    b = pkg.plugins.NeuralBSDFSampler(kind, pf, pb, precision="tc16", fixup=0.25)
+    b = pkg.plugins.NeuralBSDFSampler(kind, pf, pb, precision="tc16")
+    c = pkg.plugins.NeuralBSDFSampler(kind, pf, pb, precision="tc16")
+    cal = c.calibrate_fixup()
     ta = timed(lambda: a.sample(wi, seed=3))
     tb = timed(lambda: b.sample(wi, seed=3))
     rows = pkg.ops.last_fixup_count()
-    print("%-44s %5d %10.3f %10.3f %8.1f%% %9d (%.3f%%)" % (name, a.T, ta, tb, 100 * (tb / ta - 1), rows, 100 * rows / wi.shape[0]))
+    tc = timed(lambda: c.sample(wi, seed=3))
+    rows_c = pkg.ops.last_fixup_count() if cal["sample"] > 0 else 0
+    print("%-44s %5d %10.3f %10.3f %8.1f%% %9d (%.3f%%)   | %.4g  %.3f ms  %d (%.3f%%)" % (
+        name, a.T, ta, tb, 100 * (tb / ta - 1), rows, 100 * rows / wi.shape[0], cal["sample"], tc, rows_c, 100 * rows_c / wi.shape[0]))
