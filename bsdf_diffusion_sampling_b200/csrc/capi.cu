@@ -366,7 +366,7 @@ static int dispatch_multi(int precision, FlowParams P, int n_materials, const vo
     P.flows = reinterpret_cast<const unsigned char* const*>(flows);
     P.bases = bases;
     P.perm = v.perm; P.tiles = v.tiles; P.n_tiles_dev = v.n_tiles; P.seg_off = v.seg_off;
-    const bool fix = tc && thr > 0.0f;
+    const bool fix = tc && thr != 0.0f;               // < 0: every material's own threshold from its blob header
     if (fix) {
         P.fix_thr = thr; P.fix_count = v.fix_count; P.fix_list = v.fix_list;
         if (P.mode == kModeSample) P.fix_x0 = v.x0;                          // base samples of the flagged rows, next to the list

@@ -44,8 +44,12 @@ struct PackedHeader {
     uint32_t off_f16;     // byte offset of the fp16 image
     uint32_t f16_bytes;
     uint32_t total_bytes;
+    // reserved[0..2]: optional per-material fix-up thresholds (host: weights.PackedFlow.set_fixup): kFixThrMagic, then the
+    // conditioning thresholds of sample() and pdf() as float bits.  Read by the multi-material launches when the caller
+    // passes a NEGATIVE fix_threshold ("every material's own threshold; |fix_threshold| where a blob carries none").
     uint32_t reserved[6];
 };
+constexpr uint32_t kFixThrMagic = 0x54584946u;   // "FIXT"
 static_assert(sizeof(PackedHeader) == 64, "header must be 64 bytes");
 
 __host__ __device__ inline int f32_image_floats(int in_dim, int H, int n_hidden) {
@@ -85,7 +89,8 @@ struct FlowParams {
     // conditioning-triggered fp32 fix-up (PREC_TC16 only): the tensor-core kernel appends the row index of
     // every query whose pdf is ill-conditioned w.r.t. fp16 rounding (weight < fix_thr, see cond_weight()) to
     // fix_list[atomicAdd(fix_count)]; the CUDA-core kernel then recomputes exactly those rows in fp32
-    float fix_thr;                // 0 = off
+    float fix_thr;                // 0 = off; < 0 (multi-material launches): each material's own threshold from its blob header,
+                                  // |fix_thr| where the blob carries none (material_fix_thr)
     unsigned int* fix_count;      // device counter (zeroed by the caller before the tensor-core launch)
     unsigned int* fix_list;       // device list, capacity n
     float* fix_x0;                // [n,2] base samples of the flagged rows, parallel to fix_list (sample mode): the tensor-core
@@ -103,6 +108,15 @@ struct FlowParams {
     const unsigned int* n_tiles_dev;     // number of virtual tiles (device scalar)
     const unsigned int* seg_off;         // [n_materials + 1] first position of every material in the sorted order
 };
+
+// Conditioning threshold of tile material `mat` in a multi-material launch: P.fix_thr if positive, else the material's own
+// (PackedHeader::reserved[1 + pdf]) with |P.fix_thr| as the fallback.
+__device__ __forceinline__ float material_fix_thr(const FlowParams& P, int mat, bool pdf_mode) {
+    if (P.fix_thr >= 0.0f) return P.fix_thr;
+    const PackedHeader* h = reinterpret_cast<const PackedHeader*>(P.flows[mat]);
+    return (h->reserved[0] == kFixThrMagic) ? __uint_as_float(h->reserved[pdf_mode ? 2 : 1]) : -P.fix_thr;
+}
+
 
 // Conditioning weight in (0,1] of a query's pdf w.r.t. rounding inside the flow -- the same three factors the
 // oracle reports (oracle/bsdf_oracle.c euler(), bsdf_oracle_pdf()):  pdf = p0 (/|*) prod det_t, so an absolute error

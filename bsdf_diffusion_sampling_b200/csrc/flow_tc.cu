@@ -1335,7 +1335,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
 
             if (MODE == kModeSample) {
                 if (valid) store_sample<true>(P, i, x0, x1, p0 * R);
-                if (P.fix_thr > 0.0f) flag_for_fixup(P, valid && cond.weight() < P.fix_thr, i, MULTI ? mat : -1, theta_o, x1_start);
+                if (P.fix_thr != 0.0f)
+                    flag_for_fixup(P, valid && cond.weight() < (MULTI ? material_fix_thr(P, mat, false) : P.fix_thr), i,
+                                   MULTI ? mat : -1, theta_o, x1_start);
             } else if (MODE == kModePdf) {
                 float bp[4];
 #pragma unroll
@@ -1345,10 +1347,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) flow_tc_kernel(const FlowParams
                 if (lane == 0) mbar_arrive(smem_u32(&S.empty[sl]));
                 if (valid)
                     store_pdf<true>(P, i, __fmul_rn(__expf(base_logprob_fast<DOMAIN>(bp, x0, x1)), R), wiz, wox, woy, woz, theta_o);
-                if (P.fix_thr > 0.0f) {
+                if (P.fix_thr != 0.0f) {
                     const float kappa = (DOMAIN == kDisk) ? 0.0f : softplus_fast(bp[3]) + 1e-3f;
                     const float gn = base_grad_norm(DOMAIN, bp, kappa, x0, x1);
-                    flag_for_fixup(P, valid && cond.weight() * fminf(1.0f, __fdividef(25.0f, gn)) < P.fix_thr, i,
+                    flag_for_fixup(P, valid && cond.weight() * fminf(1.0f, __fdividef(25.0f, gn)) <
+                                          (MULTI ? material_fix_thr(P, mat, true) : P.fix_thr), i,
                                    MULTI ? mat : -1);
                 }
             } else {

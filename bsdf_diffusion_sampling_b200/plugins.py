@@ -284,12 +284,18 @@ class MultiMaterialSampler:
             if (s.kind, s.T, s.precision) != (s0.kind, s0.T, s0.precision):
                 raise ValueError("all materials of one MultiMaterialSampler must share plugin kind, T and precision")
         self.kind, self.T, self.epilogue, self.precision = s0.kind, s0.T, s0.epilogue, s0.precision
-        # one launch, one conditioning threshold: the strictest any of the materials asks for (per-material calibrated
-        # thresholds differ; None everywhere keeps following the process-wide default)
+        # thresholds: None everywhere keeps following the process-wide / family default (one value for the launch).
+        # Otherwise every material keeps its OWN thresholds: they are written into the blob headers and the launch gets a
+        # negative threshold (= "per material"; |value| = the strictest of them, used for blobs without a header entry).
         if all(s.fixup is None for s in self.samplers):
             self.fixup = None
         else:
-            self.fixup = {m: max(ops._fix_thr(s.fixup, s.domain, s.epilogue, m) for s in self.samplers)
+            own = [{m: ops._fix_thr(s.fixup, s.domain, s.epilogue, m) for m in ("sample", "pdf")} for s in self.samplers]
+            if len({id(s.flow.blob) for s in self.samplers}) != len(self.samplers):
+                raise ValueError("materials with individual fix-up thresholds need their own packed blobs")
+            for s, t in zip(self.samplers, own):
+                s.flow.set_fixup(t["sample"], t["pdf"])
+            self.fixup = {m: -max(max(t[m] for t in own), 1e-30) if any(t[m] > 0 for t in own) else 0.0
                           for m in ("sample", "pdf")}
         self.table = ops.MaterialTable([s.flow for s in self.samplers], [s.base for s in self.samplers])
 

@@ -14,6 +14,8 @@ import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Sequence
 
+import struct
+
 import numpy as np
 import torch
 
@@ -40,6 +42,19 @@ class PackedFlow:
 
     def to(self, device) -> "PackedFlow":
         return PackedFlow(self.blob.to(device), self.in_dim, self.hidden, self.n_hidden)
+
+    def set_fixup(self, sample: float, pdf: float) -> "PackedFlow":
+        """Write this material's OWN fix-up thresholds into the blob header (bytes 40..51: magic "FIXT", sample, pdf): a
+        multi-material launch called with a negative threshold recomputes, per material, only the rows below THAT material's
+        threshold (``plugins.MultiMaterialSampler`` does this when its samplers carry calibrated thresholds)."""
+        word = np.frombuffer(struct.pack("<Iff", 0x54584946, float(sample), float(pdf)), dtype=np.uint8)
+        self.blob[40:52] = torch.from_numpy(word.copy()).to(self.blob.device)
+        return self
+
+    def get_fixup(self):
+        """(sample, pdf) thresholds stored in the blob header, or None."""
+        magic, ts, tp = struct.unpack("<Iff", self.blob[40:52].cpu().numpy().tobytes())
+        return (ts, tp) if magic == 0x54584946 else None
 
 
 def _np32(t) -> np.ndarray:

@@ -183,7 +183,10 @@ int bsdfdiff_mlp_forward(int precision, int64_t n, const float* in, int in_dim, 
  * material_id:   [n] int32 (device).   scratch / plan: device buffer of bsdfdiff_multi_scratch_bytes(n, n_materials).
  * flows_packed:  DEVICE array [n_materials] of device pointers to packed flow blobs, all of one (domain, hidden,
  *                n_hidden) shape;  base_params: DEVICE array [n_materials] of device pointers to 308-float base blobs.
- * fix_threshold: as bsdfdiff_sample (the plan buffer holds the per-material fix-up lists and, when neither x0_replay
+ * fix_threshold: as bsdfdiff_sample; NEGATIVE = every material's OWN thresholds, read from its packed blob's header
+ *                (bytes 40..51: uint32 magic 0x54584946 "FIXT", float sample threshold, float pdf threshold -- written by the
+ *                host after per-material calibration), |fix_threshold| for a blob that carries none
+ *                (the plan buffer holds the per-material fix-up lists and, when neither x0_replay
  *                nor out_x0 is given, the base samples the fix-up pass replays).  n_materials <= 255, n < 2^31. */
 size_t bsdfdiff_multi_scratch_bytes(int64_t n, int n_materials);
 int bsdfdiff_multi_plan(int64_t n, const int32_t* material_id, int n_materials, void* scratch, void* cuda_stream);

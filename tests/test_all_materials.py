@@ -95,7 +95,43 @@ def test_calibrate_fixup_on_goldens(built_lib):
     wi[:, 2] = (1 - wi[:, 0] ** 2 - wi[:, 1] ** 2).clamp_min(0).sqrt()
     wo, pdf = s.sample(wi, seed=5)
     assert torch.isfinite(pdf).all() and wo.shape == (4096, 3)
-    # a multi-material launch takes the strictest threshold of its materials
-    s2 = pkg.plugins.NeuralBSDFSampler("disk", pf, pb, fixup={"sample": 0.5, "pdf": 0.125})
-    m = pkg.plugins.MultiMaterialSampler([s, s2])
-    assert m.fixup == {"sample": max(cal["sample"], 0.5), "pdf": max(cal["pdf"], 0.125)}
+
+
+@pytest.mark.gpu
+def test_multi_material_launch_keeps_per_material_thresholds(built_lib):
+    """Samplers with individual fix-up thresholds in ONE multi-material launch: every material's rows are recomputed
+    against ITS threshold (blob header + negative launch threshold) -- row-identical to the single-material calls, and
+    a material with threshold 0 recomputes nothing."""
+    import glob
+    import bsdf_diffusion_sampling_b200 as pkg
+    from conftest import GOLDEN_DIR
+    thr = [{"sample": 0.0, "pdf": 0.0}, {"sample": 0.5, "pdf": 0.7}, {"sample": 0.125, "pdf": 0.25}]
+    mats = []
+    for path, t in zip(sorted(glob.glob(os.path.join(GOLDEN_DIR, "spherical_*.npz"))), thr):
+        z = np.load(path)
+        pf = pkg.weights.pack_flow_layers([z[f"flow_w{i}"] for i in range(int(z["n_flow_layers"]))], "cuda")
+        pb = pkg.weights.pack_base_arrays(z["base_w1"], z["base_b1"], z["base_wo"], z["base_bo"], "cuda")
+        mats.append(pkg.plugins.NeuralBSDFSampler("spherical", pf, pb, fixup=dict(t)))
+    assert len(mats) == 3
+    mm = pkg.plugins.MultiMaterialSampler(mats)
+    assert mm.fixup == {"sample": -0.5, "pdf": -0.7}
+    assert [m.flow.get_fixup() for m in mats] == [(0.0, 0.0), (0.5, pytest.approx(0.7)), (0.125, 0.25)]
+    rng = np.random.default_rng(3)
+    n = 60_000
+    w = rng.normal(size=(n, 3)).astype(np.float32)
+    w[:, 2] = np.abs(w[:, 2]) + 0.05
+    wi = torch.from_numpy(w / np.linalg.norm(w, axis=1, keepdims=True)).cuda()
+    mid = torch.from_numpy(rng.integers(0, 3, n).astype(np.int32)).cuda()
+    plan = mm.plan(mid)
+    wo, pdf = mm.sample(wi, plan=plan, seed=4, offset=8)
+    fixed = plan.fixup_counts().cpu().numpy().tolist()
+    assert fixed[0] == 0 and fixed[1] > 0 and fixed[2] > 0
+    p2 = mm.pdf(wi, wo, plan=plan)
+    for m, s in enumerate(mats):
+        sel = (mid == m).nonzero().squeeze(1)
+        wo_m, pdf_m = s.sample(wi, seed=4, offset=8)
+        assert torch.equal(wo[sel], wo_m[sel]) and torch.equal(pdf[sel], pdf_m[sel]), f"material {m}"
+        assert torch.equal(p2[sel], s.pdf(wi, wo)[sel]), f"material {m} pdf()"
+    # without individual thresholds the launch keeps following the family default
+    plain = pkg.plugins.MultiMaterialSampler([pkg.plugins.NeuralBSDFSampler("spherical", m.flow, m.base) for m in mats])
+    assert plain.fixup is None
