@@ -281,6 +281,18 @@ __device__ __forceinline__ void tmem_ld8_pack16(uint32_t taddr, uint32_t* r) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                  : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld4_pack16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.pack::16b.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float& a, float& b) {
     uint32_t x, y;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(taddr) : "memory");
@@ -406,6 +418,31 @@ __device__ __forceinline__ void activate16(const float* z, const uint32_t* du, c
             pu[j >> 1] = hmul2_(s16, du[j >> 1]);
             pv[j >> 1] = hmul2_(s16, dv[j >> 1]);
         }
+    }
+}
+
+// BSDFDIFF_TC_PIPE4 (tuning build): the pass over 32 neurons as four chunks of 8, software-pipelined so that the MUFU ops of
+// chunk c+1 execute under the half2 tail of chunk c (the shipped pass runs two bursts of 16 MUFU ops, each followed by
+// the tail that depends on it).
+#ifndef BSDFDIFF_TC_PIPE4
+#define BSDFDIFF_TC_PIPE4 0
+#endif
+__device__ __forceinline__ void tanh8(const float* z, float* t) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = tanh_approx(z[j]);
+}
+__device__ __forceinline__ void tail8(const float* z, const float* t, const uint32_t* du, const uint32_t* dv,
+                                      uint32_t* ph, uint32_t* pu, uint32_t* pv) {
+    constexpr uint32_t kOneH2 = 0x3C003C00u;
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+        const f32x2 zh = pk2(z[j], z[j + 1]);
+        const uint32_t h16 = pack_h2(fma2(zh, pk2(t[j], t[j + 1]), zh));
+        const uint32_t t16 = pack_h2(t[j], t[j + 1]);
+        const uint32_t s16 = hfma2_(h16, hsub2_(kOneH2, t16), hadd2_(kOneH2, t16));
+        ph[j >> 1] = h16;
+        pu[j >> 1] = hmul2_(s16, du[j >> 1]);
+        pv[j >> 1] = hmul2_(s16, dv[j >> 1]);
     }
 }
 
@@ -781,6 +818,34 @@ __device__ __forceinline__ void activation_pass(uint32_t tg, uint32_t av_row, in
             activate16<false, ACT>(zc[c & 1], nullptr, nullptr, ph, nullptr, nullptr);
             tmem_st8(tg + col_ah<H>() + 8 * c, ph);
         }
+        return;
+    }
+    if (BSDFDIFF_TC_PIPE4 && TANGENTS && ACT == 1 && !kSmemAv) {
+        float z[4][8], t[2][8];
+        uint32_t du[4][4], dv[4][4], ph[4], pu[4], pv[4];
+        auto ld = [&](int c) {
+            tmem_ld8(tg + kColDz + 8 * c, z[c]);
+            tmem_ld4_pack16(tg + kColDu + 8 * c, du[c]);
+            tmem_ld4_pack16(tg + kColDv + 8 * c, dv[c]);
+        };
+        auto st = [&](int c) {
+            tmem_st4(tg + col_ah<H>() + 4 * c, ph[0], ph[1], ph[2], ph[3]);
+            tmem_st4(tg + kColAu + 4 * c, pu[0], pu[1], pu[2], pu[3]);
+            tmem_st4(tg + kColAv + 4 * c, pv[0], pv[1], pv[2], pv[3]);
+        };
+        // A_u (columns kColAu + 0..15) overlaps D_v's FIRST 16 columns only = chunks 0 and 1, which are in registers after the
+        // first wait::ld: every store below is safe
+        ld(0); ld(1);
+        tc_wait_ld();
+        ld(2);
+        tanh8(z[0], t[0]);
+        tanh8(z[1], t[1]); tail8(z[0], t[0], du[0], dv[0], ph, pu, pv); st(0);
+        tc_wait_ld();
+        ld(3);
+        tanh8(z[2], t[0]); tail8(z[1], t[1], du[1], dv[1], ph, pu, pv); st(1);
+        tc_wait_ld();
+        tanh8(z[3], t[1]); tail8(z[2], t[0], du[2], dv[2], ph, pu, pv); st(2);
+        tail8(z[3], t[1], du[3], dv[3], ph, pu, pv); st(3);
         return;
     }
     float za[16], zb[16];
