@@ -135,3 +135,35 @@ def test_multi_material_launch_keeps_per_material_thresholds(built_lib):
     # without individual thresholds the launch keeps following the family default
     plain = pkg.plugins.MultiMaterialSampler([pkg.plugins.NeuralBSDFSampler("spherical", m.flow, m.base) for m in mats])
     assert plain.fixup is None
+
+
+@pytest.mark.gpu
+def test_material_pack_calibrate_round_trip(built_lib, tmp_path):
+    """MaterialPack.calibrate stores every material's own thresholds; they survive save / load, reach the samplers and
+    the multi-material sampler (per-material thresholds in one launch)."""
+    import glob
+    import bsdf_diffusion_sampling_b200 as pkg
+    from bsdf_diffusion_sampling_b200.materials import MaterialPack
+    from conftest import GOLDEN_DIR
+    pack = MaterialPack()
+    for path in sorted(glob.glob(os.path.join(GOLDEN_DIR, "spherical_*.npz"))):
+        z = np.load(path)
+        base = np.concatenate([z[k].ravel() for k in ("base_w1", "base_b1", "base_wo", "base_bo")])
+        pack.add(os.path.basename(path)[10:-4], "spherical", [z[f"flow_w{i}"] for i in range(int(z["n_flow_layers"]))], base)
+    cal = pack.calibrate(n_side=128)
+    assert set(cal) == set(pack.names()) and all(set(v) == {"sample", "pdf"} for v in cal.values())
+    assert cal["ilm_solo_m_68_rgb"]["sample"] > cal["aniso_brushed_aluminium_1_rgb"]["sample"]   # the ill-conditioned golden
+    path = str(tmp_path / "scene.bsdfpack")
+    pack.save(path)
+    back = MaterialPack.load(path)
+    for name in back.names():
+        assert back.sampler(name).fixup == cal[name]
+    mm = back.multi_sampler()
+    assert mm.fixup["sample"] == -max(c["sample"] for c in cal.values())
+    wi = torch.from_numpy(np.tile(np.array([[0.3, -0.2, 0.93]], np.float32), (4096, 1))).cuda()
+    mid = torch.arange(4096, dtype=torch.int32).cuda() % len(back.names())
+    wo, pdf = mm.sample(wi, mid, seed=3)
+    for m, name in enumerate(back.names()):
+        sel = (mid == m).nonzero().squeeze(1)
+        wo_m, pdf_m = back.sampler(name).sample(wi, seed=3)
+        assert torch.equal(wo[sel], wo_m[sel]) and torch.equal(pdf[sel], pdf_m[sel])
