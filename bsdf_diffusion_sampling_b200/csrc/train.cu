@@ -25,6 +25,8 @@
 #include "common.cuh"
 #include "train.cuh"
 
+#include <cstdlib>
+
 namespace bsdfdiff {
 
 __device__ __forceinline__ void silu_both(float z, float& h, float& g) {
@@ -334,6 +336,226 @@ __global__ void __launch_bounds__(ROWS) flow_matching_step_kernel(const TrainPar
 }
 
 // ------------------------------------------------------------------------------------------------
+// 32-wide nets, TWO threads per row.  Every row keeps 188 floats of pre-activations in shared memory, so an SM holds
+// ~256 rows whatever the tile shape: with one thread per row that is 8 warps per SM (2 per scheduler), and the kernel
+// above waits on its own shared-memory loads (ncu: issue slots 43 % busy, short-scoreboard stalls).  Here thread
+// (row, half) owns 16 of the 32 neurons of every layer -- half the FMAs of the forward / backward products per thread,
+// the same shared-memory footprint, twice the warps.  The halves of a row sit in different warps (half = tid / ROWS is
+// warp-uniform), meet through the shared-memory columns (one __syncthreads per layer) and recompute silu(z) of the row's
+// layer input redundantly in the forward product.  Sums run in the same order as in the one-thread kernel except the
+// two-row output layer (two 16-term partial sums).
+// ------------------------------------------------------------------------------------------------
+template <int ROWS, int RS, int THREADS, int SLOTS>
+__device__ __forceinline__ void tile_outer_t(const float* __restrict__ D, int J, const float* __restrict__ P, int K,
+                                             float (*acc)[4]) {
+    const int kb = (K + 3) >> 2;
+#pragma unroll
+    for (int sl = 0; sl < SLOTS; ++sl) {        // work item o = tid + sl * THREADS of the J * kb (<= 256) of a layer
+        const int o = threadIdx.x + sl * THREADS;
+        if (o < J * kb) tile_outer_one<ROWS, RS>(D, P, K, o, acc[sl]);
+    }
+}
+
+template <int ROWS>
+__global__ void __launch_bounds__(2 * ROWS, 2) flow_matching_step_pair_kernel(const TrainParams P) {
+    constexpr int H = 32, HH = 16, THREADS = 2 * ROWS;
+    extern __shared__ __align__(16) float smem[];
+    const int in_dim = P.in_dim, L = P.n_hidden;
+    const int n_w = in_dim * H + (L - 1) * H * H + 2 * H;
+    constexpr int RS = TrainSmem<H, ROWS>::RS;
+    constexpr int kMaxL = 4;
+    float* Wt = smem;                                    // transposed image: W1t [in][H], W2t.. [H][H], Woutt [H][2]
+    float* col = smem + ((n_w + 3) & ~3);
+    float* Z = col;                                      // [L][H][RS]
+    float* IN = Z + (size_t)L * H * RS;                  // [kIn][RS]
+    float* D = IN + (size_t)TrainSmem<H, ROWS>::kIn * RS;   // [H][RS]  delta_z of the current layer (rows 2..5: output-layer partial sums)
+    float* HP = D + (size_t)H * RS;                      // [H][RS]  input of the current layer (h_{l-1})
+    const int tid = threadIdx.x;
+    const int half = tid / ROWS, row = tid - half * ROWS, jb = half * HH;
+    constexpr int SLOTS = (H * (H / 4) + THREADS - 1) / THREADS;      // 1 (256 threads) or 2 (192 threads: 96-row tiles)
+    float gacc[kMaxL][SLOTS][4], gout[1][4];             // this thread's work items of dW_1..dW_L and dWout, summed over the CTA's tiles
+#pragma unroll
+    for (int l = 0; l < kMaxL; ++l)
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) gacc[l][sl][0] = gacc[l][sl][1] = gacc[l][sl][2] = gacc[l][sl][3] = 0.0f;
+    gout[0][0] = gout[0][1] = gout[0][2] = gout[0][3] = 0.0f;
+    {   // stage the weights, transposed (torch layout [out][in] -> [in][out])
+        const float* w = P.weights;
+        float* t = Wt;
+        for (int l = 0; l <= L; ++l) {
+            const int R = (l == L) ? 2 : H, C = (l == 0) ? in_dim : H;
+            for (int i = tid; i < R * C; i += THREADS) { const int j = i / C, k = i - j * C; t[k * R + j] = w[i]; }
+            w += R * C; t += R * C;
+        }
+    }
+    __syncthreads();
+
+    const long long n = P.n;
+    const long long n_tiles = (n + ROWS - 1) / ROWS;
+    const float inv_nm1 = (n > 1) ? 1.0f / (float)(n - 1) : 0.0f;
+    const float inv_n = 1.0f / (float)n;
+    float loss_acc = 0.0f;
+
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long i = tile * ROWS + row;
+        const bool valid = i < n;
+        const long long ic = valid ? i : n - 1;
+        // ---- inputs: half 0 the state columns and the regression target, half 1 PE5(wi) -----------------------------------
+        float t0 = 0.0f, t1 = 0.0f;
+        const int k0 = (P.domain == kDisk) ? 3 : 4;
+        if (half == 0) {
+            const float2 a = reinterpret_cast<const float2*>(P.x0)[ic];
+            float2 b = reinterpret_cast<const float2*>(P.x1)[ic];
+            const float alpha = P.alpha ? P.alpha[ic] : (float)ic * inv_nm1;
+            t0 = b.x - a.x; t1 = b.y - a.y;
+            if (P.domain == kDisk) {
+                IN[0 * RS + row] = (1.0f - alpha) * a.x + alpha * b.x;
+                IN[1 * RS + row] = (1.0f - alpha) * a.y + alpha * b.y;
+                IN[2 * RS + row] = alpha;
+            } else {
+                const float kPi = 3.14159265358979323846f, kTwoPi = 6.28318530717958647692f;
+                if (t1 < -kPi) { b.y += kTwoPi; t1 += kTwoPi; } else if (t1 > kPi) { b.y -= kTwoPi; t1 -= kTwoPi; }
+                const float th = (1.0f - alpha) * a.x + alpha * b.x, ph = (1.0f - alpha) * a.y + alpha * b.y;
+                float sn, cs;
+                sincosf(ph, &sn, &cs);
+                IN[0 * RS + row] = th; IN[1 * RS + row] = sn; IN[2 * RS + row] = cs; IN[3 * RS + row] = alpha;
+            }
+        } else {
+            const float2 wi = reinterpret_cast<const float2*>(P.wi)[ic];
+            float e[kPE5];
+            positional_encoding<5>(wi.x, wi.y, e);
+#pragma unroll
+            for (int k = 0; k < kPE5; ++k) IN[(k0 + k) * RS + row] = e[k];
+        }
+        __syncthreads();
+
+        // ---- forward: this thread's 16 neurons of every layer ------------------------------------------------------------
+        // h_l = silu(z_l) is written next to z_l by the thread that owns the neuron (HP and D take turns as the layer-input
+        // buffer; the last layer lands in HP, which the backward pass expects), so the product loop below is loads + FMAs only
+        const float* Wl = Wt;
+        for (int l = 0; l < L; ++l) {
+            const int K = (l == 0) ? in_dim : H;
+            float az[HH];
+#pragma unroll
+            for (int j = 0; j < HH; ++j) az[j] = 0.0f;
+            const float* hin = (l == 0) ? IN : (((L - l) & 1) ? D : HP);
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const float hk = hin[k * RS + row];
+                const float4* w4 = reinterpret_cast<const float4*>(Wl + k * H + jb);
+#pragma unroll
+                for (int j4 = 0; j4 < HH / 4; ++j4) {
+                    const float4 w = w4[j4];
+                    az[4 * j4 + 0] = fmaf(hk, w.x, az[4 * j4 + 0]);
+                    az[4 * j4 + 1] = fmaf(hk, w.y, az[4 * j4 + 1]);
+                    az[4 * j4 + 2] = fmaf(hk, w.z, az[4 * j4 + 2]);
+                    az[4 * j4 + 3] = fmaf(hk, w.w, az[4 * j4 + 3]);
+                }
+            }
+            float* zo = Z + (size_t)l * H * RS;
+            float* ho = ((L - 1 - l) & 1) ? D : HP;
+#pragma unroll
+            for (int j = 0; j < HH; ++j) {
+                zo[(jb + j) * RS + row] = az[j];
+                ho[(jb + j) * RS + row] = az[j] * sigmoid_newton(az[j]);
+            }
+            Wl += K * H;
+            __syncthreads();                              // the row's other half of z_l / h_l
+        }
+        // ---- output layer + loss: each half sums its 16 neurons of h_L (in HP); D rows 0..1 <- delta_out -----------------
+        const float* zl = Z + (size_t)(L - 1) * H * RS;
+        {
+            float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll 4
+            for (int kk = 0; kk < HH; ++kk) {
+                const int k = jb + kk;
+                const float h = HP[k * RS + row];
+                const float2 w = reinterpret_cast<const float2*>(Wl)[k];
+                q0 = fmaf(h, w.x, q0); q1 = fmaf(h, w.y, q1);
+            }
+            D[(2 + 2 * half) * RS + row] = q0; D[(3 + 2 * half) * RS + row] = q1;
+        }
+        __syncthreads();
+        const float p0 = D[2 * RS + row] + D[4 * RS + row], p1 = D[3 * RS + row] + D[5 * RS + row];
+        // half 1 does not know the target: half 0 publishes delta_out, both read it back
+        if (half == 0) {
+            float d0 = valid ? (p0 - t0) : 0.0f, d1 = valid ? (p1 - t1) : 0.0f;
+            loss_acc += 0.5f * (d0 * d0 + d1 * d1);
+            D[0 * RS + row] = d0 * inv_n; D[1 * RS + row] = d1 * inv_n;
+        }
+        __syncthreads();
+        const float d0 = D[0 * RS + row], d1 = D[1 * RS + row];
+
+        // ---- backward ----------------------------------------------------------------------------------------------------
+        tile_outer_t<ROWS, RS, THREADS, 1>(D, 2, HP, H, gout);              // dWout [2][H]
+        float dz[HH];                                                         // delta_z of the last hidden layer, my 16 neurons
+#pragma unroll
+        for (int kk = 0; kk < HH; ++kk) {
+            const int k = jb + kk;
+            const float2 w = reinterpret_cast<const float2*>(Wl)[k];
+            float h, g;
+            silu_both(zl[k * RS + row], h, g);
+            dz[kk] = (d0 * w.x + d1 * w.y) * g;
+        }
+        for (int l = L - 1; l >= 0; --l) {
+            const int K = (l == 0) ? in_dim : H;
+            const int off = (l == 0) ? 0 : in_dim * H + (l - 1) * H * H;
+            __syncthreads();                              // everyone is done reading D / HP of the layer above
+#pragma unroll
+            for (int j = 0; j < HH; ++j) D[(jb + j) * RS + row] = dz[j];
+            const float* src = (l == 0) ? IN : Z + (size_t)(l - 1) * H * RS;
+            if (l > 0) {
+#pragma unroll 4
+                for (int kk = 0; kk < HH; ++kk) { const float z = src[(jb + kk) * RS + row]; HP[(jb + kk) * RS + row] = z * sigmoid_newton(z); }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < kMaxL; ++q)               // the layer index selects the register block at compile time
+                if (q == l) tile_outer_t<ROWS, RS, THREADS, SLOTS>(D, H, (l == 0) ? IN : HP, K, gacc[q]);
+            if (l > 0) {
+                // delta_h_{l-1}[k] = sum_j Wt_l[k][j] delta_z_l[j] over ALL 32 j (the other half's come from D), for my 16 k
+                const float* Wc = Wt + off;
+                float dzf[H];
+#pragma unroll
+                for (int j = 0; j < H; ++j) dzf[j] = D[j * RS + row];
+                float nz[HH];
+#pragma unroll 4
+                for (int kk = 0; kk < HH; ++kk) {
+                    const int k = jb + kk;
+                    const float4* w4 = reinterpret_cast<const float4*>(Wc + k * H);
+                    float acc = 0.0f;
+#pragma unroll
+                    for (int j4 = 0; j4 < H / 4; ++j4) {
+                        const float4 w = w4[j4];
+                        acc = fmaf(w.x, dzf[4 * j4 + 0], acc); acc = fmaf(w.y, dzf[4 * j4 + 1], acc);
+                        acc = fmaf(w.z, dzf[4 * j4 + 2], acc); acc = fmaf(w.w, dzf[4 * j4 + 3], acc);
+                    }
+                    float h, g;
+                    silu_both(src[k * RS + row], h, g);
+                    nz[kk] = acc * g;
+                }
+#pragma unroll
+                for (int kk = 0; kk < HH; ++kk) dz[kk] = nz[kk];
+            }
+        }
+        __syncthreads();                                  // the next tile overwrites IN / Z / D / HP
+    }
+
+    // ---- this CTA's gradient sums -> global gradient (one atomic per weight per CTA) ---------------------------------
+#pragma unroll
+    for (int q = 0; q < kMaxL; ++q)
+        if (q < L) {
+            const int K = (q == 0) ? in_dim : H, kb = (K + 3) >> 2;
+#pragma unroll
+            for (int sl = 0; sl < SLOTS; ++sl)
+                if (tid + sl * THREADS < H * kb)
+                    add_outer_one(K, tid + sl * THREADS, gacc[q][sl], P.grad + ((q == 0) ? 0 : in_dim * H + (q - 1) * H * H));
+        }
+    if (tid < 2 * (H / 4)) add_outer_one(H, tid, gout[0], P.grad + in_dim * H + (L - 1) * H * H);
+    finish_step<THREADS>(P, n_w, loss_acc * inv_n);
+}
+
+// ------------------------------------------------------------------------------------------------
 // pretrain stage: negative log-likelihood of the base distribution (disk_domain_sampling.py:14-33,
 // spherical_domain_sampling.py:16-35):  loss = -mean(D_base.log_prob(omega_o, omega_i));  Adam.
 // Base net 14 -> 16 -> 4 with biases (model.py:374-398 disk, :277-317 spherical); parameters in the 308-float base-blob
@@ -488,8 +710,29 @@ static int launch_train_t(const TrainParams& P, cudaStream_t stream) {
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
 
+template <int ROWS>
+static int launch_train_pair_t(const TrainParams& P, cudaStream_t stream) {
+    const size_t smem = sizeof(float) * TrainSmem<32, ROWS>::floats(P.in_dim, P.n_hidden) + 16;
+    if (smem > 227u * 1024u) return -2;
+    auto kern = flow_matching_step_pair_kernel<ROWS>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -3;
+    int dev = 0, sms = 0, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 2 * ROWS, smem) != cudaSuccess || occ < 1) return -3;
+    long long tiles = (P.n + ROWS - 1) / ROWS, grid = (long long)sms * occ;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+    kern<<<(unsigned)grid, 2 * ROWS, smem, stream>>>(P);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
 int launch_flow_matching_step(const TrainParams& P, cudaStream_t stream) {
     if (P.n_hidden < 1) return -2;
+    // 32-wide nets with up to 4 hidden layers: two threads per row (BSDFDIFF_TRAIN_PAIR=0 selects the one-thread kernel for A/B runs)
+    static const bool pair = [] { const char* e = getenv("BSDFDIFF_TRAIN_PAIR"); return !(e && e[0] == '0'); }();
+    if (pair && P.hidden == 32 && P.n_hidden <= 4)
+        return P.n_hidden <= 3 ? launch_train_pair_t<128>(P, stream) : launch_train_pair_t<96>(P, stream);
     // 32-wide nets: 128-row tiles while two CTAs fit an SM (3 hidden layers: 111 KB each); with 4 hidden layers a 128-row
     // CTA needs 133 KB (one per SM), 96-row tiles need 104 KB (two per SM: 6 warps instead of 4)
     if (P.hidden == 32) return P.n_hidden <= 3 ? launch_train_t<32, 128>(P, stream)
