@@ -33,15 +33,23 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b,
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) { tmem_st4(taddr, r[0], r[1], r[2], r[3]); tmem_st4(taddr + 4, r[4], r[5], r[6], r[7]); }
+// FORM 0: shipped.  1: h from two scalar FFMAs (FMA-lite capable) instead of one FFMA2.  2: (1 - t), (1 + t) from four scalar FADDs and two
+// packs instead of pack(t) + two HADD2.  3: both.
+#ifndef FORM
+#define FORM 0
+#endif
 __device__ __forceinline__ void activate16(const float* z, const uint32_t* du, const uint32_t* dv, uint32_t* ph, uint32_t* pu, uint32_t* pv) {
     constexpr uint32_t kOneH2 = 0x3C003C00u;
 #pragma unroll
     for (int j = 0; j < 16; j += 2) {
         const float t0 = tanh_approx(z[j]), t1 = tanh_approx(z[j + 1]);
-        const f32x2 zh = pk2(z[j], z[j + 1]);
-        const uint32_t h16 = pack_h2(fma2(zh, pk2(t0, t1), zh));
-        const uint32_t t16 = pack_h2(t0, t1);
-        const uint32_t s16 = hfma2_(h16, hsub2_(kOneH2, t16), hadd2_(kOneH2, t16));
+        uint32_t h16;
+        if (FORM & 1) h16 = pack_h2(fmaf(z[j], t0, z[j]), fmaf(z[j + 1], t1, z[j + 1]));
+        else { const f32x2 zh = pk2(z[j], z[j + 1]); h16 = pack_h2(fma2(zh, pk2(t0, t1), zh)); }
+        uint32_t a16, b16;
+        if (FORM & 2) { a16 = pack_h2(1.0f - t0, 1.0f - t1); b16 = pack_h2(1.0f + t0, 1.0f + t1); }
+        else { const uint32_t t16 = pack_h2(t0, t1); a16 = hsub2_(kOneH2, t16); b16 = hadd2_(kOneH2, t16); }
+        const uint32_t s16 = hfma2_(h16, a16, b16);
         ph[j >> 1] = h16; pu[j >> 1] = hmul2_(s16, du[j >> 1]); pv[j >> 1] = hmul2_(s16, dv[j >> 1]);
     }
 }
@@ -107,7 +115,8 @@ __global__ void __launch_bounds__(512, 1) k(int nwarps, int with_tmem, long long
 int main() {
     long long* out; cudaMallocManaged(&out, 32 * sizeof(long long));
     const char* names[4] = {"math only (registers)     ", "tcgen05.ld + math         ", "math + tcgen05.st         ", "full pass (ld, math, st)  "};
-    for (int with_tmem = 3; with_tmem >= 0; --with_tmem)
+    printf("FORM %d\n", FORM);
+    for (int with_tmem = 3; with_tmem >= 3; --with_tmem)
         for (int w : {4, 8, 12, 16}) {
             k<<<148, 512>>>(w, with_tmem, out);
             if (cudaDeviceSynchronize() != cudaSuccess) { printf("failed: %s\n", cudaGetErrorString(cudaGetLastError())); return 1; }
